@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""
+bench.py — layer x wavelength-bin two-stream flux evaluations per second.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+One "step" = one radiative-equilibrium iteration (emit sweep + absorb sweep,
+each with its (P,T) brackets, opacity gather, two-stream layer response,
+wavelength integrals, cross-GPU sum and temperature update) of BASELINE.json
+config C2: hot Jupiter, 50 layers x 200k wavelength bins, 3 opacity species,
+synthetic seeded tables, fp64.  One iteration = 2 (L-1) n_lambda evaluations.
+With N > 1 GPUs the wavelength axis is sharded, 200k bins per GPU (weak
+scaling), with an NCCL all-reduce of the [L][4] integrals after every sweep.
+
+--impl reference times the reference's CPU arithmetic (the numpy+scipy oracle:
+the reference itself cannot be installed here or on the GPU box — astropy,
+xarray, specutils, pyfastchem are absent and there is no network) on all host
+cores, same workload, same metric.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = 'layer-lambda-bin two-stream flux evaluations/s'
+UNIT = 'evals/s'
+L_C2, NLAM_C2, S_C2, TREF_C2 = 50, 200_000, 3, 2400.0
+
+
+def read_peaks():
+    path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    try:
+        with open(path) as fh:
+            return float(json.load(fh)['hbm_gbs']), 'measured (MEASURED_PEAKS.json hbm_gbs)'
+    except Exception:
+        return 6650.0, 'fallback (B200_PROFILING.md 6.65 TB/s)'
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,'
+         'clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+         'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                 '-i', str(self.index), '-lms', '100'],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons, power = [], None, set(), []
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax = float(f[2])
+                power.append(float(f[3]))
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown',
+                                  'sw_power_cap'), f[5:9]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': smax,
+                'reasons': sorted(reasons), 'samples': len(sm),
+                'power_w_max': max(power) if power else None}
+
+
+# ---------------------------------------------------------------------------
+# CPU arms (the oracle is the checker/baseline, never the product)
+# ---------------------------------------------------------------------------
+def cpu_baseline_one_core(seconds_target=12.0):
+    """Oracle on ONE core over a bounded sample of C2: 2 iterations on a 50k-bin slice."""
+    from oracle.parallel import ParallelOracle
+    n_sample = 50_000
+    po = ParallelOracle((L_C2, NLAM_C2, S_C2, TREF_C2), n_workers=1, n_lam_sample=n_sample)
+    po.iteration()                                   # warm-up (page in, caches)
+    t0 = time.perf_counter()
+    n_it = 0
+    while n_it < 2 or (time.perf_counter() - t0 < seconds_target and n_it < 6):
+        po.iteration()
+        n_it += 1
+    dt = time.perf_counter() - t0
+    return {'value': po.evals_per_iteration * n_it / dt, 'unit': UNIT, 'cores': 1, 'kind': 'port',
+            'sample': f'{n_it} RE iterations on the first {n_sample} of {NLAM_C2} bins of C2 '
+                      f'(50 layers, 3 species), numpy+scipy oracle, 1 process'}
+
+
+def run_reference(args):
+    """--impl reference: oracle on all host cores, C2 grid, one iteration per step."""
+    rank = int(os.environ.get('RANK', '0'))
+    if rank != 0:
+        return
+    from oracle.parallel import ParallelOracle, available_cores
+    cores = available_cores()
+    workers = max(1, min(cores, 64))
+    n_lam = NLAM_C2 if workers >= 4 else 25_000 * workers
+    po = ParallelOracle((L_C2, NLAM_C2, S_C2, TREF_C2), n_workers=workers, n_lam_sample=n_lam)
+    for _ in range(args.warmup):
+        po.iteration()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        po.iteration()
+    dt = time.perf_counter() - t0
+    po.close()
+    value = po.evals_per_iteration * args.steps / dt
+    sample = (f'one RE iteration per step on {n_lam} of {NLAM_C2} bins of C2, wavelength axis '
+              f'split over {workers} processes (numpy+scipy oracle of the reference arithmetic)')
+    print(json.dumps({
+        'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT,
+        'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+        'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'C2: hot Jupiter, 50 layers x 200k lambda bins, 3 species '
+                               '(H2O+CO+CH4 synthetic tables), fp64', 'bins_timed': n_lam},
+        'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port',
+                         'sample': sample},
+        'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }))
+
+
+# ---------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from frei_b200 import synthetic
+    from frei_b200.core import Grid, Planet
+    from frei_b200.engine import Engine, FREI_EMIT, FREI_ABSORB, FREI_F32, FREI_F64, shard_range
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    group = None
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+        group = dist.group.WORLD
+    if args.gpus != world and rank == 0:
+        print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
+
+    L, S = L_C2, S_C2
+    n_lam_global = NLAM_C2 * world                         # weak scaling: 200k bins per GPU
+    tdtype = FREI_F32 if args.table_dtype == 32 else FREI_F64
+    w = synthetic.make_workload(L, n_lam_global, S, TREF_C2, table_f32=(tdtype == FREI_F32))
+    lo, hi = shard_range(n_lam_global, rank, world)
+    table = synthetic.device_table(w, tdtype, lam_range=(lo, hi), device=dev)
+    pl = w['planet']
+    eng = Engine(table, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'],
+                 m_bar=pl['m_bar'], alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+                 group=group)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        eng.sweep(FREI_EMIT)
+        eng.sweep(FREI_ABSORB)
+
+    for _ in range(args.warmup):
+        step()
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.25)
+    eng.sweep_events = []
+    launches0 = eng.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync()
+    ev0.record()
+    for _ in range(args.steps):
+        step()
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    sweep_ms = [a.elapsed_time(b) for a, b in eng.sweep_events]
+    eng.sweep_events = None
+    launches = eng.launches - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    evals_per_step = 2 * (L - 1) * n_lam_global
+    value = evals_per_step * args.steps / (ms * 1e-3)
+
+    # roofline of the dominant kernel (the layer sweep), this rank's launches
+    b_tab = 4 if tdtype == FREI_F32 else 8
+    bytes_per_eval = 4 * S * b_tab + 3 * 8
+    sweep_avg_ms = float(np.mean(sweep_ms))
+    algo_bytes = (L - 1) * (hi - lo) * bytes_per_eval
+    peak, peak_src = read_peaks()
+    achieved = algo_bytes / (sweep_avg_ms * 1e-3) / 1e9
+
+    # e2e through the public API: Grid.emission_spectrum with host buffers
+    e2e = None
+    try:
+        planet = Planet(a_rstar=pl['a_rstar'], m_bar=pl['m_bar'], g=pl['g'] / 100.0,
+                        T_star=pl['T_star'], alpha=pl['alpha'])
+        grid = Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
+        grid.attach_device_table(table, species=w['species'])
+        k_e2e = max(2, args.steps)
+        grid.emission_spectrum(n_timesteps=2, n_zero_crossings=10 ** 9, convergence_dT=0, group=group)
+        sync()
+        t0 = time.perf_counter()
+        grid.emission_spectrum(n_timesteps=k_e2e, n_zero_crossings=10 ** 9, convergence_dT=0,
+                               group=group)
+        sync()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        n_loc = hi - lo
+        h2d = (8 * n_lam_global + 8 * L * (2 + S) + 8 * 3) / k_e2e
+        d2h = 3 * L * 8 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e
+        e2e = {'value': (2 * k_e2e + 1) * (L - 1) * n_lam_global / dt, 'unit': UNIT,
+               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+               'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}) incl. setup, per-iteration '
+                       'T/dT read-back + host convergence test, final emit, spectrum+dtaus D2H',
+               'seconds': dt}
+    except Exception as exc:                                   # pragma: no cover
+        e2e = {'value': None, 'error': repr(exc)}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_one_core()
+
+    if rank == 0:
+        out = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
+            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {
+                'workload': ('C2: hot Jupiter, 50 layers x 200k lambda bins per GPU, 3 species '
+                             '(H2O+CO+CH4 synthetic tables), one RE iteration (emit+absorb) per step'),
+                'n_layers': L, 'n_lambda_global': n_lam_global, 'n_species': S,
+                'table_dtype': f'f{args.table_dtype}', 'flux_dtype': 'f64',
+                'parallelism': f'lambda-sharded x{world}' if world > 1 else 'single GPU',
+                'l2': 'inputs larger than L2: flux state 160 MB + table '
+                      f'{table.values.numel() * b_tab / 1e6:.0f} MB per GPU touched every step',
+            },
+            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
+                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'kernel': 'sweep_kernel', 'kernel_avg_ms': sweep_avg_ms,
+                         'bytes_per_eval': bytes_per_eval,
+                         'kernel_share_of_step': 2 * sweep_avg_ms / (ms / args.steps)},
+            'cpu_baseline': cpu,
+            'e2e': e2e,
+            'gpu_launches': launches,
+            'clocks': clocks,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=20)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--table-dtype', type=int, default=64, choices=[32, 64])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
+    if args.impl == 'reference':
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == '__main__':
+    main()

@@ -1,0 +1,330 @@
+"""
+User-facing driver — same interface as ``frei/core.py`` (``Planet``, ``Grid``,
+``effective_temperature``).  ``Grid.emission_spectrum`` keeps the reference's
+host control flow (outer loop, convergence test, final emit,
+frei/core.py:263-338) and runs every sweep on the GPU with the flux state,
+tables and per-wavelength constants resident in HBM; only T and dT
+(``n_layers`` doubles each) cross PCIe per iteration.
+"""
+import numpy as np
+
+from . import _cabi
+from . import units as U
+from .chemistry import chemistry
+from .engine import Engine, DeviceTable, FREI_EMIT, FREI_ABSORB, FREI_F64, shard_range
+from .tp import pressure_grid, temperature_grid
+
+__all__ = ['Grid', 'Planet', 'effective_temperature', 'Spectrum']
+
+
+def wavelength_grid(min_micron=0.5, max_micron=10, n_bins=500, lam=None):
+    """Log-spaced wavelength grid, bin edges and resolution (frei/core.py:34-45)."""
+    if lam is None:
+        lam_um = np.logspace(np.log10(min_micron), np.log10(max_micron), n_bins)
+    else:
+        lam_um = U.value(lam, 'um')
+    wl_bins = np.concatenate([[lam_um.min() - (lam_um[1] - lam_um[0])], lam_um]) \
+        + (lam_um[1] - lam_um[0]) / 2
+    mid = lam_um.shape[0] // 2
+    R = float(lam_um[mid] / (lam_um[mid + 1] - lam_um[mid]))
+    return U.wrap(lam_um, 'um'), wl_bins, R
+
+
+def _spectral_host(lam_um, m_bar_g, T_star, a_rstar, f=2 / 3):
+    """Run the spectral_setup kernel and return its five arrays on the host."""
+    import torch
+    lib = _cabi.load()
+    _cabi.require_cuda()
+    dev = torch.device('cuda', torch.cuda.current_device())
+    lam_um = np.ascontiguousarray(lam_um, dtype=np.float64)
+    n = lam_um.shape[0]
+    d_lam = torch.from_numpy(lam_um).to(dev)
+    outs = [torch.empty(n, dtype=torch.float64, device=dev) for _ in range(5)]
+    _cabi.check(lib.frei_b200_spectral_setup(
+        d_lam.data_ptr(), n, 0, n, float(m_bar_g), float(T_star), float(a_rstar), float(f),
+        *[o.data_ptr() for o in outs], torch.cuda.current_stream(dev).cuda_stream))
+    return [o.cpu().numpy() for o in outs]
+
+
+def BB(temperature):
+    """Planck function factory, B_lambda without the steradian (frei/twostream.py:46-67)."""
+    T = float(U.value(temperature, 'K'))
+
+    def bb(wavelength):
+        lam_um = np.atleast_1d(U.value(wavelength, 'um'))
+        c1, c2, _, _, _ = _spectral_host(lam_um, 2.4 * U.m_p, T, 1.0)
+        return U.wrap(c1 / np.expm1(c2 / T), 'flux')
+    return bb
+
+
+def B_star(T_star, lam):
+    """Blackbody spectrum of the star (frei/core.py:58-62)."""
+    return BB(T_star)(lam)
+
+
+def F_TOA(lam, T_star=5800, f=2 / 3, a_rstar=0.03 * U.au / U.R_sun):
+    """Stellar flux at the top of the atmosphere (frei/core.py:48-55)."""
+    lam_um = np.atleast_1d(U.value(lam, 'um'))
+    out = _spectral_host(lam_um, 2.4 * U.m_p, float(U.value(T_star, 'K')), float(a_rstar), f)
+    return U.wrap(out[4], 'flux')
+
+
+class Planet(object):
+    """Container for planetary system information (frei/core.py:65-106)."""
+
+    def __init__(self, a_rstar, m_bar, g, T_star, alpha):
+        self.a_rstar = a_rstar
+        self.m_bar = m_bar
+        self.g = g
+        self.T_star = T_star
+        self.alpha = alpha
+
+    @classmethod
+    def from_hot_jupiter(cls):
+        """M = M_J, R = R_J, m_bar = 2.4 m_p, T_star = 5800 K, a = 0.03 au (frei/core.py:92-106)."""
+        g_cgs = U.GM_jup / U.R_jup ** 2
+        return cls(a_rstar=float(0.03 * U.au / U.R_sun),
+                   m_bar=U.wrap(2.4 * U.m_p, 'g'),
+                   g=U.wrap(g_cgs / 100.0, 'm/s2'),
+                   T_star=U.wrap(5800.0, 'K'),
+                   alpha=1)
+
+
+class Spectrum(object):
+    """Fallback for ``specutils.Spectrum1D`` (frei/core.py:335-337): flux + spectral axis."""
+
+    def __init__(self, flux, spectral_axis):
+        self.flux = flux
+        self.spectral_axis = spectral_axis
+
+    @property
+    def wavelength(self):
+        return self.spectral_axis
+
+
+def _make_spectrum(flux, lam):
+    try:                                                    # pragma: no cover
+        from specutils import Spectrum1D
+        return Spectrum1D(flux=flux, spectral_axis=lam)
+    except ImportError:
+        return Spectrum(flux, lam)
+
+
+def converged_layers(temp_hists, dT, n_zero_crossings, convergence_dT):
+    """
+    Per-layer convergence flags of the outer loop (frei/core.py:306-311): more
+    than ``n_zero_crossings`` sign flips of the temperature history differences,
+    or the last absorb step below ``convergence_dT``.
+    """
+    temp_hist = np.hstack(temp_hists)
+    temp_hist = temp_hist.T[temp_hist[0] != 0].T
+    diffs = np.diff(temp_hist.T, axis=0)
+    flips = np.count_nonzero(np.sign(diffs[1:]) != np.sign(diffs[:-1]), axis=0)
+    return (flips > n_zero_crossings) | (np.abs(dT) < convergence_dT), temp_hist
+
+
+class Grid(object):
+    """Grid over temperatures, pressures and wavelengths (frei/core.py:109-338)."""
+
+    def __init__(self, planet, lam=None, pressures=None, init_temperatures=None,
+                 lam_min=0.5, lam_max=10, n_wl_bins=500,
+                 P_toa=1e-6, P_boa=200, n_layers=30,
+                 T_ref=2300, P_ref=0.1, alpha=0.1):
+        self.planet = planet
+        if lam is None:
+            self.lam, self.wl_bins, self.R = wavelength_grid(
+                min_micron=float(U.value(lam_min, 'um')),
+                max_micron=float(U.value(lam_max, 'um')), n_bins=n_wl_bins)
+        else:
+            self.lam, self.wl_bins, self.R = wavelength_grid(lam=lam)
+        if pressures is None:
+            self.pressures = pressure_grid(
+                n_layers=n_layers, P_toa=np.log10(float(U.value(P_toa, 'bar'))),
+                P_boa=np.log10(float(U.value(P_boa, 'bar'))))
+        else:
+            self.pressures = pressures
+        if init_temperatures is None:
+            self.init_temperatures = temperature_grid(self.pressures, T_ref, P_ref, alpha)
+        else:
+            self.init_temperatures = init_temperatures
+        self.opacities = None
+        self._table = None
+        self.table_dtype = FREI_F64
+
+    def __repr__(self):
+        T = U.value(self.init_temperatures, 'K')
+        P = U.value(self.pressures, 'bar')
+        lam = U.value(self.lam, 'um')
+        return (f"<Grid in T=[{T[0]:.0f}...{T[-1]:.0f}] K, p=[{P[0]:.2g}...{P[-1]:.2g}] bar, "
+                f"lam=[{lam[0]}...{lam[-1]}] um>")
+
+    def load_opacities(self, species=None, path=None, opacities=None, client=None,
+                       force_reload=False, groupies=False):
+        """
+        Attach opacity tables (frei/core.py:198-231).  Pre-computed tables are
+        passed with ``opacities=``; they are uploaded to the GPU on first use.
+        """
+        if (self.opacities is None and opacities is None) or force_reload:
+            from .opacity import binned_opacity
+            self.opacities = binned_opacity(self.init_temperatures, self.pressures,
+                                            self.wl_bins, self.lam, species=species,
+                                            groupies=groupies, path=path)
+        else:
+            self.opacities = opacities
+        self._table = None
+        return self.opacities
+
+    # -- device residency -----------------------------------------------------
+    def attach_device_table(self, table, species=None):
+        """
+        Use tables that already live in HBM (a :class:`~frei_b200.engine.DeviceTable`
+        holding this rank's wavelength slice) instead of uploading host arrays.
+        """
+        self.opacities = {k: None for k in (species or table.species)}
+        self._table = table
+        self._table_key = 'attached'
+        return self.opacities
+
+    def device_table(self, group=None):
+        if getattr(self, '_table_key', None) == 'attached':
+            return self._table
+        lam_range = None
+        if group is not None:
+            import torch.distributed as dist
+            n = U.value(self.lam, 'um').shape[0]
+            lam_range = shard_range(n, dist.get_rank(group), dist.get_world_size(group))
+        if self._table is None or self._table_key != (lam_range, self.table_dtype):
+            self._table = DeviceTable(self.opacities, dtype=self.table_dtype, lam_range=lam_range)
+            self._table_key = (lam_range, self.table_dtype)
+        return self._table
+
+    def _mmr(self, T, P, m_bar_g):
+        species = list(self.opacities.keys())
+        d = chemistry(T, P, species, m_bar=m_bar_g)
+        return np.stack([np.broadcast_to(d[s], T.shape) for s in species], axis=-1)
+
+    def make_engine(self, group=None, want_dtaus=False):
+        pl = self.planet
+        T0 = U.value(self.init_temperatures, 'K')
+        P = U.value(self.pressures, 'bar')
+        m_bar_g = float(U.value(pl.m_bar, 'g'))
+        return Engine(self.device_table(group), U.value(self.lam, 'um'), P, T0,
+                      self._mmr(T0, P, m_bar_g), g=U.gravity_cgs(pl.g), m_bar=m_bar_g,
+                      alpha=pl.alpha, T_star=float(U.value(pl.T_star, 'K')),
+                      a_rstar=float(pl.a_rstar), group=group, want_dtaus=want_dtaus)
+
+    def emission_spectrum(self, n_timesteps=1, n_zero_crossings=2, convergence_dT=3,
+                          group=None, dynamic_chemistry=None):
+        """
+        Iterate emit/absorb sweeps towards radiative equilibrium and return
+        ``(spectrum, final_temps, temperature_history, dtaus)`` exactly as
+        frei/core.py:233-338.  ``group`` shards the wavelength axis over a
+        torch.distributed process group (every rank returns the full result).
+        ``dynamic_chemistry``: recompute mixing ratios from the current T before
+        every sweep (default: only when pyfastchem is installed; the mock's
+        ratios do not depend on T).
+        """
+        import torch
+        if self.opacities is None:
+            raise ValueError("Must load opacities before computing emission spectrum.")
+        conv_dT = float(U.value(convergence_dT, 'K'))
+        if dynamic_chemistry is None:
+            try:
+                import pyfastchem  # noqa: F401
+                dynamic_chemistry = True
+            except ImportError:
+                dynamic_chemistry = False
+        eng = self.make_engine(group=group)
+        P = U.value(self.pressures, 'bar')
+        m_bar_g = float(U.value(self.planet.m_bar, 'g'))
+        L = eng.L
+        hist_dev = torch.empty((3, 1, L), dtype=torch.float64, device=eng.device)
+        hist_host = torch.empty((3, 1, L), dtype=torch.float64).pin_memory()
+        temp_hists = []
+        self.n_iterations = 0
+        for it in range(n_timesteps):
+            if dynamic_chemistry and it > 0:
+                eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
+            eng.sweep(FREI_EMIT, T_hist=hist_dev[0])
+            if dynamic_chemistry:
+                eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
+            eng.sweep(FREI_ABSORB, T_hist=hist_dev[1])
+            hist_dev[2].copy_(eng.dT)
+            hist_host.copy_(hist_dev, non_blocking=True)
+            torch.cuda.current_stream(eng.device).synchronize()
+            h = hist_host.numpy()
+            temp_hists.append(np.stack([h[0, 0], h[1, 0]], axis=1).copy())
+            dT = h[2, 0].copy()
+            self.n_iterations += 1
+            conv, _ = converged_layers(temp_hists, dT, n_zero_crossings, conv_dT)
+            if np.all(conv):
+                break
+        temp_hist = np.hstack(temp_hists) if temp_hists else np.zeros((L, 0))
+        if temp_hists:
+            temp_hist = temp_hist.T[temp_hist[0] != 0].T
+        if dynamic_chemistry and n_timesteps > 0:
+            eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
+        # final emit: alpha is not forwarded -> default 1 (frei/core.py:323-333)
+        eng.sweep(FREI_EMIT, alpha_override=1.0, with_dtaus=True)
+        final_temps = eng.T[0].cpu().numpy()
+        spec_local = eng.F_up[0, L - 1]
+        dtaus_local = eng.dtaus[0]
+        if group is not None:
+            spec, dtaus = _gather_lambda(spec_local, dtaus_local, eng, group)
+        else:
+            spec, dtaus = spec_local.cpu().numpy(), dtaus_local.cpu().numpy()
+        self.engine = eng
+        return (_make_spectrum(U.wrap(spec, 'flux'), self.lam), U.wrap(final_temps, 'K'),
+                U.wrap(temp_hist, 'K'), dtaus)
+
+    def emission_dashboard(self, *args, **kwargs):
+        raise NotImplementedError('plotting is outside the scope of frei_b200 (frei/plot.py)')
+
+
+def _gather_lambda(spec_local, dtaus_local, eng, group):
+    """All-gather wavelength slices (uneven sizes) of the final spectrum and dtaus."""
+    import torch
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+    n = eng.n_lam_global
+    sizes = [shard_range(n, r, world) for r in range(world)]
+    nmax = max(hi - lo for lo, hi in sizes)
+    L = eng.L
+    buf = torch.zeros((L + 1, nmax), dtype=torch.float64, device=eng.device)
+    buf[0, :eng.n_lam] = spec_local
+    buf[1:, :eng.n_lam] = dtaus_local
+    out = [torch.empty_like(buf) for _ in range(world)]
+    dist.all_gather(out, buf, group=group)
+    spec = np.concatenate([o[0, :hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)])
+    dtaus = np.concatenate([o[1:, :hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)],
+                           axis=1)
+    return spec, dtaus
+
+
+# -- T_eff diagnostics (frei/core.py:386-439): cheap host post-processing ----------
+def effective_temperature_milne(grid, spec, dtaus, final_temps):
+    """Photosphere temperature from Milne's tau ~ 2/3 (frei/core.py:386-405)."""
+    lam_um = U.value(grid.lam, 'um')
+    P = U.value(grid.pressures, 'bar')
+    T = U.value(final_temps, 'K')
+    flux = U.value(spec.flux, 'flux')
+    pressure_milne = np.ones_like(lam_um)
+    for i in range(dtaus.shape[1]):
+        pressure_milne[i] = np.interp(2 / 3, np.exp(-dtaus[:, i]), P)
+    p_avg = np.average(pressure_milne, weights=flux * (lam_um * 1e-4))
+    return U.wrap(np.interp(p_avg, P[::-1], T[::-1]), 'K')
+
+
+def effective_temperature_planck(grid, spec):
+    """Invert the Stefan-Boltzmann law for the emitted bolometric flux (frei/core.py:408-414)."""
+    lam_cm = U.value(grid.lam, 'um') * 1e-4
+    flux = U.value(spec.flux, 'flux')
+    trapz = getattr(np, 'trapezoid', None) or np.trapz
+    return U.wrap((trapz(flux, lam_cm) / U.sigma_sb) ** (1 / 4), 'K')
+
+
+def effective_temperature(grid, spec, dtaus, final_temps):
+    """Mean of the Milne and Stefan-Boltzmann estimates (frei/core.py:417-439)."""
+    a = float(U.value(effective_temperature_milne(grid, spec, dtaus, final_temps), 'K'))
+    b = float(U.value(effective_temperature_planck(grid, spec), 'K'))
+    return U.wrap(np.mean([a, b]), 'K')

@@ -1,0 +1,333 @@
+"""
+Device-resident state of the radiative-equilibrium hot path and the thin layer
+that drives the C ABI (``include/frei_b200.h``).  PyTorch is used only for
+device buffers, streams and ``torch.distributed``; all arithmetic on the path
+runs in the CUDA kernels of ``csrc/frei_b200.cu``.
+
+Layout in HBM (one GPU):
+  table   [S][N_P][N_T][n_lam_local]   fp32 or fp64, wavelength contiguous
+  F_up, F_down (, dtaus)  [B][L][n_lam_local]   fp64
+  c1, c2, sigma, w, f_toa [n_lam_local] fp64
+  T, P [B][L]; mmr [B][L][S]; g, m_bar, alpha [B]        fp64
+Wavelength sharding: every rank holds a contiguous slice of the wavelength axis
+of every array above; T/P/mmr are replicated and the [B][L][4] wavelength
+integrals are summed across ranks once per sweep.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _cabi
+from ._cabi import FREI_EMIT, FREI_ABSORB, FREI_F32, FREI_F64
+
+__all__ = ['DeviceTable', 'Engine', 'FREI_EMIT', 'FREI_ABSORB', 'shard_range']
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def shard_range(n, rank, world):
+    """Contiguous slice [lo, hi) of an axis of length n owned by ``rank`` of ``world``."""
+    base, rem = divmod(int(n), int(world))
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def normalise_table(tab):
+    """
+    Bring one species' table to (P_axis ascending [bar], T_axis ascending [K],
+    values[N_P, N_T, n_lam], has_T).  Accepts the oracle-style dict(P=, T=,
+    values=) or an xarray.DataArray-like object with ``pressure``,
+    ``temperature`` coords and ``dims`` (frei/opacity.py:331-339, 467-477).
+    """
+    if isinstance(tab, dict):
+        Pax = np.asarray(tab['P'], dtype=np.float64)
+        Tax = np.asarray(tab['T'], dtype=np.float64)
+        vals = np.asarray(tab['values'])
+    else:
+        Pax = np.asarray(getattr(tab.pressure, 'values', tab.pressure), dtype=np.float64)
+        Tax = np.asarray(getattr(tab.temperature, 'values', tab.temperature), dtype=np.float64)
+        Tax = np.asarray(getattr(Tax, 'value', Tax), dtype=np.float64)
+        vals = np.asarray(getattr(tab, 'values'))
+        dims = tuple(getattr(tab, 'dims', ('pressure', 'temperature', 'wavelength')))
+        order = [dims.index(d) for d in ('pressure', 'temperature', 'wavelength')]
+        vals = np.transpose(vals, order)
+    ip = np.argsort(Pax, kind='stable')
+    it = np.argsort(Tax, kind='stable')
+    Pax, Tax = Pax[ip], Tax[it]
+    vals = vals[ip][:, it]
+    has_T = len(np.unique(Tax)) > 1                    # frei/opacity.py:256
+    if not has_T:
+        Tax = np.array([Tax[0], Tax[0] + 1.0])
+        vals = np.repeat(vals[:, :1], 2, axis=1)
+    return Pax, Tax, vals, has_T
+
+
+class DeviceTable:
+    """Opacity tables of all species as one dense device block (see ``frei_table``)."""
+
+    def __init__(self, opacities, device=None, dtype=FREI_F64, lam_range=None):
+        torch = _torch()
+        _cabi.require_cuda()
+        self.device = torch.device('cuda', torch.cuda.current_device()) if device is None \
+            else torch.device(device)
+        items = list(opacities.items()) if isinstance(opacities, dict) else \
+            [(str(i), t) for i, t in enumerate(opacities)]
+        self.species = [k for k, _ in items]
+        norm = [normalise_table(t) for _, t in items]
+        N_P = {n[0].shape[0] for n in norm}
+        N_T = {n[1].shape[0] for n in norm if n[3]}
+        if len(N_P) != 1 or len(N_T) > 1:
+            raise ValueError('all species tables must share the (pressure, temperature) grid sizes')
+        self.N_P = N_P.pop()
+        self.N_T = N_T.pop() if N_T else 2
+        self.S = len(norm)
+        n_lam_global = norm[0][2].shape[2]
+        lo, hi = (0, n_lam_global) if lam_range is None else lam_range
+        self.lam_range = (lo, hi)
+        self.n_lam = hi - lo
+        self.dtype = dtype
+        tdt = torch.float32 if dtype == FREI_F32 else torch.float64
+        ndt = np.float32 if dtype == FREI_F32 else np.float64
+        self.values = torch.empty((self.S, self.N_P, self.N_T, self.n_lam), dtype=tdt,
+                                  device=self.device)
+        axP = np.empty((self.S, self.N_P))
+        axT = np.empty((self.S, self.N_T))
+        hasT = np.empty(self.S, dtype=np.int32)
+        for s, (Pax, Tax, vals, has_T) in enumerate(norm):
+            if not has_T and self.N_T > 2:
+                Tax = Tax[0] + np.arange(self.N_T, dtype=np.float64)
+                vals = np.repeat(vals[:, :1], self.N_T, axis=1)
+            axP[s], axT[s], hasT[s] = Pax, Tax, int(has_T)
+            chunk = np.ascontiguousarray(vals[:, :, lo:hi], dtype=ndt)
+            self.values[s].copy_(torch.from_numpy(chunk))
+        self.axis_P = torch.from_numpy(axP).to(self.device)
+        self.axis_T = torch.from_numpy(axT).to(self.device)
+        self.has_T = torch.from_numpy(hasT).to(self.device)
+
+    @classmethod
+    def from_device_values(cls, values, axis_P, axis_T, has_T=None, species=None):
+        """Wrap an existing device tensor [S][N_P][N_T][n_lam] (no copy)."""
+        torch = _torch()
+        self = cls.__new__(cls)
+        self.device = values.device
+        self.S, self.N_P, self.N_T, self.n_lam = values.shape
+        self.lam_range = (0, self.n_lam)
+        self.dtype = FREI_F32 if values.dtype == torch.float32 else FREI_F64
+        self.values = values.contiguous()
+        axP = np.broadcast_to(np.asarray(axis_P, dtype=np.float64), (self.S, self.N_P))
+        axT = np.broadcast_to(np.asarray(axis_T, dtype=np.float64), (self.S, self.N_T))
+        self.axis_P = torch.from_numpy(np.ascontiguousarray(axP)).to(self.device)
+        self.axis_T = torch.from_numpy(np.ascontiguousarray(axT)).to(self.device)
+        hT = np.ones(self.S, dtype=np.int32) if has_T is None else np.asarray(has_T, dtype=np.int32)
+        self.has_T = torch.from_numpy(hT).to(self.device)
+        self.species = species or [str(i) for i in range(self.S)]
+        return self
+
+    def struct(self):
+        return _cabi.frei_table(self.values.data_ptr(), self.axis_P.data_ptr(),
+                                self.axis_T.data_ptr(), self.has_T.data_ptr(),
+                                self.S, self.N_P, self.N_T, self.dtype, self.n_lam)
+
+
+class Engine:
+    """
+    B atmospheres x L levels x n_lam wavelengths resident on one GPU.
+
+    Parameters are plain numbers/arrays in the units of ``include/frei_b200.h``
+    (T [K], P [bar], g [cm s^-2], m_bar [g], wavelength [micron]).
+    ``lam_um`` is the GLOBAL grid; ``table`` holds the slice ``table.lam_range``.
+    ``group``: a torch.distributed process group over which the wavelength
+    axis is sharded (None = single device / independent batches).
+    """
+
+    def __init__(self, table, lam_um, pressures_bar, temperatures, mmr, g, m_bar, alpha=1.0,
+                 T_star=5800.0, a_rstar=1.0, f_toa=None, ftoa_scale=None, group=None,
+                 flux_dtype=FREI_F64, want_dtaus=False):
+        torch = _torch()
+        self.lib = _cabi.load()
+        _cabi.require_cuda()
+        self.table = table
+        self.device = dev = table.device
+        self.group = group
+        f64 = torch.float64
+        P = np.atleast_2d(np.asarray(pressures_bar, dtype=np.float64))
+        T = np.atleast_2d(np.asarray(temperatures, dtype=np.float64))
+        self.B, self.L = P.shape
+        if self.L < 3:
+            raise ValueError('need at least 3 levels')
+        self.S = table.S
+        lam_um = np.ascontiguousarray(lam_um, dtype=np.float64)
+        self.n_lam_global = lam_um.shape[0]
+        self.lo, self.hi = table.lam_range
+        self.n_lam = table.n_lam
+        B, L, S, n = self.B, self.L, self.S, self.n_lam
+
+        def dvec(x, shape):
+            a = np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), shape))
+            return torch.from_numpy(a.copy()).to(dev)
+
+        self.P = dvec(P, (B, L))
+        self.T = dvec(T, (B, L))
+        self.mmr = dvec(mmr, (B, L, S))
+        self.g = dvec(g, (B,))
+        m_bar_b = np.broadcast_to(np.asarray(m_bar, dtype=np.float64), (B,))
+        self.m_bar = dvec(m_bar_b, (B,))
+        self.alpha = dvec(alpha, (B,))
+        self.sigma_scale = None
+        if not np.all(m_bar_b == m_bar_b[0]):
+            self.sigma_scale = dvec(m_bar_b[0] / m_bar_b, (B,))
+        self.ftoa_scale = None if ftoa_scale is None else dvec(ftoa_scale, (B,))
+
+        # per-wavelength constants (K: spectral_setup)
+        self.lam_dev = torch.from_numpy(lam_um).to(dev)
+        self.c1, self.c2, self.sigma, self.w, self.f_toa = (
+            torch.empty(n, dtype=f64, device=dev) for _ in range(5))
+        _cabi.check(self.lib.frei_b200_spectral_setup(
+            self.lam_dev.data_ptr(), self.n_lam_global, self.lo, n, float(m_bar_b[0]),
+            float(T_star), float(a_rstar), 2.0 / 3.0, self.c1.data_ptr(), self.c2.data_ptr(),
+            self.sigma.data_ptr(), self.w.data_ptr(), self.f_toa.data_ptr(), self._stream()))
+        if f_toa is not None:       # caller-supplied F_TOA (emit()/absorb() signature)
+            f_toa = np.ascontiguousarray(f_toa, dtype=np.float64)
+            self.f_toa.copy_(torch.from_numpy(f_toa[self.lo:self.hi]))
+
+        # flux state
+        if flux_dtype != FREI_F64:
+            raise NotImplementedError('fp32 flux state is not implemented yet')
+        self.flux_dtype = flux_dtype
+        self.F_up = torch.zeros((B, L, n), dtype=f64, device=dev)
+        self.F_down = torch.zeros((B, L, n), dtype=f64, device=dev)
+        self.dtaus = torch.empty((B, L, n), dtype=f64, device=dev) if want_dtaus else None
+
+        # workspace
+        sizes = [C.c_int64() for _ in range(4)]
+        _cabi.check(self.lib.frei_b200_workspace_bytes(B, L, S, n, *[C.byref(s) for s in sizes]))
+        self._lp = torch.empty(sizes[0].value, dtype=torch.uint8, device=dev)
+        self._partials = torch.empty(sizes[1].value // 8, dtype=f64, device=dev)
+        self.sums = torch.zeros((B, L, 4), dtype=f64, device=dev)
+        self.dT = torch.zeros((B, L), dtype=f64, device=dev)
+        self.launches = 0
+        self.sweep_events = None        # list of (start, end) CUDA events around the sweep kernel
+        self._build_structs()
+
+    # -- plumbing -----------------------------------------------------------
+    def _stream(self):
+        return _torch().cuda.current_stream(self.device).cuda_stream
+
+    def _build_structs(self):
+        n = self.n_lam
+        self._tab = self.table.struct()
+        self._spec = _cabi.frei_spectral(self.c1.data_ptr(), self.c2.data_ptr(),
+                                         self.sigma.data_ptr(), self.w.data_ptr(),
+                                         self.f_toa.data_ptr(), n)
+        self._atm = _cabi.frei_atmosphere(
+            self.T.data_ptr(), self.P.data_ptr(), self.mmr.data_ptr(), self.g.data_ptr(),
+            self.m_bar.data_ptr(), self.alpha.data_ptr(), _cabi.ptr(self.sigma_scale),
+            _cabi.ptr(self.ftoa_scale), self.B, self.L)
+        self._ws = _cabi.frei_workspace(self._lp.data_ptr(), self._partials.data_ptr(),
+                                        self.sums.data_ptr(), self.dT.data_ptr())
+
+    def _flux_struct(self, with_dtaus):
+        return _cabi.frei_flux(self.F_up.data_ptr(), self.F_down.data_ptr(),
+                               _cabi.ptr(self.dtaus) if with_dtaus else None, self.flux_dtype)
+
+    # -- state --------------------------------------------------------------
+    def set_T(self, T):
+        torch = _torch()
+        self.T.copy_(torch.from_numpy(np.ascontiguousarray(
+            np.broadcast_to(np.asarray(T, dtype=np.float64), (self.B, self.L)))))
+
+    def set_mmr(self, mmr):
+        torch = _torch()
+        self.mmr.copy_(torch.from_numpy(np.ascontiguousarray(
+            np.broadcast_to(np.asarray(mmr, dtype=np.float64), (self.B, self.L, self.S)))))
+
+    def set_fluxes(self, F_up=None, F_down=None):
+        """Upload the local wavelength slice of host flux arrays [B?][L][n_lam_global]."""
+        torch = _torch()
+        for dst, src in ((self.F_up, F_up), (self.F_down, F_down)):
+            if src is not None:
+                a = np.asarray(src, dtype=np.float64).reshape((self.B, self.L, -1))
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(a[:, :, self.lo:self.hi])))
+
+    def get_T(self):
+        return self.T.cpu().numpy()
+
+    # -- kernels ------------------------------------------------------------
+    def layer_prep(self, debug=False):
+        torch = _torch()
+        out = None
+        args = [None] * 5
+        if debug:
+            shp = (self.B, self.L, self.S)
+            out = dict(iP=torch.empty(shp, dtype=torch.int32, device=self.device),
+                       iT=torch.empty(shp, dtype=torch.int32, device=self.device),
+                       wP=torch.empty(shp, dtype=torch.float64, device=self.device),
+                       wT=torch.empty(shp, dtype=torch.float64, device=self.device),
+                       oob=torch.empty(shp, dtype=torch.uint8, device=self.device))
+            args = [out[k].data_ptr() for k in ('iP', 'iT', 'wP', 'wT', 'oob')]
+        _cabi.check(self.lib.frei_b200_layer_prep(C.byref(self._tab), C.byref(self._atm),
+                                                  C.byref(self._ws), *args, self._stream()))
+        self.launches += 1
+        return out
+
+    def kappa(self):
+        """k[B][L][n_lam] and sigma[B][n_lam] at the current (T, P) of every level."""
+        torch = _torch()
+        self.layer_prep()
+        k = torch.empty((self.B, self.L, self.n_lam), dtype=torch.float64, device=self.device)
+        sg = torch.empty((self.B, self.n_lam), dtype=torch.float64, device=self.device)
+        _cabi.check(self.lib.frei_b200_kappa(C.byref(self._tab), C.byref(self._spec),
+                                             C.byref(self._atm), C.byref(self._ws),
+                                             k.data_ptr(), sg.data_ptr(), self._stream()))
+        self.launches += 1
+        return k, sg
+
+    def sweep(self, direction, alpha_override=-1.0, with_dtaus=False, T_hist=None):
+        """
+        One emit (FREI_EMIT) or absorb (FREI_ABSORB) pass: brackets, layer sweep,
+        wavelength integrals, (cross-rank sum,) temperature update.  Everything
+        is enqueued on the current stream; nothing is synchronised.
+        """
+        if with_dtaus and self.dtaus is None:
+            torch = _torch()
+            self.dtaus = torch.empty((self.B, self.L, self.n_lam), dtype=torch.float64,
+                                     device=self.device)
+        flux = self._flux_struct(with_dtaus)
+        st = self._stream()
+        hist_ptr = None if T_hist is None else T_hist.data_ptr()
+        if self.group is None and self.sweep_events is None:
+            _cabi.check(self.lib.frei_b200_sweep_step(
+                C.byref(self._tab), C.byref(self._spec), C.byref(self._atm), C.byref(flux),
+                direction, float(alpha_override), C.byref(self._ws), hist_ptr, st))
+            self.launches += 4
+            return
+        _cabi.check(self.lib.frei_b200_layer_prep(C.byref(self._tab), C.byref(self._atm),
+                                                  C.byref(self._ws), None, None, None, None,
+                                                  None, st))
+        if self.sweep_events is not None:
+            torch = _torch()
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record()
+        _cabi.check(self.lib.frei_b200_sweep(C.byref(self._tab), C.byref(self._spec),
+                                             C.byref(self._atm), C.byref(flux), direction,
+                                             C.byref(self._ws), st))
+        if self.sweep_events is not None:
+            ev[1].record()
+            self.sweep_events.append(ev)
+        _cabi.check(self.lib.frei_b200_reduce(C.byref(self._atm), C.byref(self._ws),
+                                              self.n_lam, st))
+        if self.group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
+        _cabi.check(self.lib.frei_b200_update_T(C.byref(self._atm), C.byref(self._ws), direction,
+                                                float(alpha_override), hist_ptr, st))
+        self.launches += 4
+
+    def emit(self, **kw):
+        self.sweep(FREI_EMIT, **kw)
+
+    def absorb(self, **kw):
+        self.sweep(FREI_ABSORB, **kw)

@@ -1,0 +1,192 @@
+/*
+ * frei_b200.h — C ABI of the B200-native radiative-equilibrium hot path.
+ *
+ * The reference (bmorris3/frei) is pure Python and defines no FFI; the
+ * functions below are what a ctypes binding in the reference would call in
+ * place of the Python bodies cited next to each entry point (paths are into
+ * the reference checkout, `frei/...`).  INTEGRATION.md shows that binding.
+ *
+ * Rules of the boundary
+ *   - extern "C", plain pointers and sizes, no C++/torch types.
+ *   - Every pointer named d_* / documented "device" is device memory owned by
+ *     the caller (e.g. a torch allocation); the library only borrows it for
+ *     the duration of the (asynchronous) call.  `stream` is a cudaStream_t
+ *     passed as void* (NULL = legacy default stream).
+ *   - All functions return 0 on success and a negative FREI_E_* code on
+ *     failure; frei_b200_last_error() returns the message of the last failure
+ *     on the calling thread.  Nothing is thrown across the boundary.
+ *   - There is no CPU fallback: without a CUDA device every compute entry
+ *     point fails with FREI_E_CUDA.
+ *
+ * Units: T [K]; P [bar] (frei/tp.py:32, table axis frei/opacity.py:253);
+ * g [cm s^-2]; m_bar [g]; wavelength-derived constants in CGS; fluxes
+ * [erg s^-1 cm^-3] (frei/twostream.py:13); opacities [cm^2 g^-1].
+ * Layer index 0 = bottom of the atmosphere (highest pressure).
+ */
+#ifndef FREI_B200_H
+#define FREI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FREI_B200_ABI_VERSION 1
+
+enum {
+    FREI_OK = 0,
+    FREI_E_ARG = -1,      /* bad argument (null pointer, size, dtype, L < 3, ...) */
+    FREI_E_CUDA = -2,     /* CUDA runtime error; see frei_b200_last_error()      */
+    FREI_E_UNSUPPORTED = -3
+};
+
+enum { FREI_EMIT = 0, FREI_ABSORB = 1 };     /* sweep direction */
+enum { FREI_F32 = 32, FREI_F64 = 64 };       /* storage dtypes  */
+
+/* Opacity tables of all S species, one dense block, wavelength contiguous:
+ * values[s][iP][iT][j].  Replaces the dict of xarray.DataArray handed to
+ * kappa() (frei/opacity.py:203-209, 250-263).  Axes are ascending (xarray
+ * sorts before interpolating).  has_T[s] == 0 reproduces the
+ * "single unique temperature -> interpolate in pressure only" branch
+ * (frei/opacity.py:256); such a species still occupies N_T (>= 2) rows. */
+typedef struct {
+    const void*    values;     /* device, S*N_P*N_T*n_lam elements of `dtype`      */
+    const double*  axis_P;     /* device [S][N_P], bar                             */
+    const double*  axis_T;     /* device [S][N_T], K                               */
+    const int32_t* has_T;      /* device [S]                                       */
+    int32_t        S, N_P, N_T;
+    int32_t        dtype;      /* FREI_F32 | FREI_F64                              */
+    int64_t        n_lam;      /* wavelength bins held by this device (row length) */
+} frei_table;
+
+/* Per-wavelength constants of this device's wavelength range.
+ * c1 = 2 h c^2 / lam^5 and c2 = h c / (lam k_B) give Planck
+ * B = c1 / expm1(c2 / T) (frei/twostream.py:64-67); sigma = Rayleigh H2+He
+ * (frei/opacity.py:187-200, 233); w = trapezoid weights of the GLOBAL grid so
+ * sum_j w_j F_j == np.trapz(F, lam) (frei/twostream.py:16-20) even when the
+ * grid is sharded; f_toa = stellar flux (frei/core.py:48-55). */
+typedef struct {
+    const double* c1;
+    const double* c2;
+    const double* sigma;
+    const double* w;
+    const double* f_toa;
+    int64_t       n_lam;
+} frei_spectral;
+
+/* B independent atmospheres of L levels each. */
+typedef struct {
+    double*       T;            /* device [B][L], in/out                               */
+    const double* P;            /* device [B][L], bar, bottom -> top                   */
+    const double* mmr;          /* device [B][L][S] mass-mixing ratios = the output of
+                                   chemistry() (frei/opacity.py:246-248)               */
+    const double* g;            /* device [B]                                          */
+    const double* m_bar;        /* device [B]                                          */
+    const double* alpha;        /* device [B], mixing-length parameter                 */
+    const double* sigma_scale;  /* device [B] or NULL: sigma_b = sigma * scale_b       */
+    const double* ftoa_scale;   /* device [B] or NULL: F_TOA_b = f_toa * scale_b       */
+    int32_t       B, L;
+} frei_atmosphere;
+
+/* Flux state, mutated in place like the reference's fluxes_up / fluxes_down
+ * (frei/twostream.py:392-394, 521-522). */
+typedef struct {
+    void*   F_up;      /* device [B][L][n_lam]                                         */
+    void*   F_down;    /* device [B][L][n_lam]                                         */
+    void*   dtaus;     /* device [B][L][n_lam] or NULL; row order as the reference
+                          returns it (frei/twostream.py:352, 374, 487, 505)            */
+    int32_t dtype;     /* FREI_F32 | FREI_F64 (also selects the arithmetic type)       */
+} frei_flux;
+
+/* Scratch owned by the caller; sizes from frei_b200_workspace_bytes(). */
+typedef struct {
+    void*   layer_params;  /* written by layer_prep, read by kappa / sweep */
+    double* partials;      /* written by sweep, read by reduce             */
+    double* sums;          /* [B][L][4]: wavelength integrals of F2_up, F2_down, F1_up,
+                              F1_down per layer-step (the four bolometric_flux calls,
+                              frei/twostream.py:396-398, 524-527)          */
+    double* dT;            /* [B][L] temperature change of the last sweep  */
+} frei_workspace;
+
+const char* frei_b200_last_error(void);
+int  frei_b200_abi_version(void);
+int  frei_b200_device_count(void);
+
+/* Bytes needed for each workspace member (any out pointer may be NULL). */
+int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
+                              int64_t* layer_params, int64_t* partials,
+                              int64_t* sums, int64_t* dT);
+
+/* Per-wavelength constants of the slice [offset, offset + n_local) of the global
+ * grid d_lam_um[n_global] (micron, ascending): fills a frei_spectral's arrays.
+ * Covers BB prefactors (frei/twostream.py:64-67), rayleigh_H2 + rayleigh_He
+ * (frei/opacity.py:173-200, 233, pure functions of wavelength the reference
+ * recomputes every layer-step), np.trapz weights (frei/twostream.py:16-20) and
+ * F_TOA (frei/core.py:48-62) with f = 2/3. */
+int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t offset,
+                             int64_t n_local, double m_bar, double T_star, double a_rstar,
+                             double f, double* d_c1, double* d_c2, double* d_sigma,
+                             double* d_w, double* d_f_toa, void* stream);
+
+/* K0.  Bracket (P_i, T_i) of every level in every species' axes with the rule
+ * of scipy.interpolate's find_indices (reached from frei/opacity.py:261-263),
+ * build mmr-premultiplied corner weights (zero when out of bounds:
+ * fill_value=0, frei/opacity.py:241-244) and the per-layer scalars
+ * (p1-p2)/g (frei/twostream.py:227-231) and 1/T.
+ * Optional device outputs for bit-exact index tests, each [B][L][S] or NULL:
+ * iP, iT (int32), wP, wT (double), oob (uint8). */
+int frei_b200_layer_prep(const frei_table* tab, const frei_atmosphere* atm,
+                         const frei_workspace* ws,
+                         int32_t* d_iP, int32_t* d_iT, double* d_wP, double* d_wT,
+                         uint8_t* d_oob, void* stream);
+
+/* K1 (standalone).  k[b][i][j] = sum_s mmr * bilerp(table_s) + sigma, and
+ * sigma_out[b][j]: kappa() for every level at once (frei/opacity.py:203-269).
+ * Requires layer_prep.  d_k: [B][L][n_lam] doubles, d_sigma: [B][n_lam] doubles. */
+int frei_b200_kappa(const frei_table* tab, const frei_spectral* spec,
+                    const frei_atmosphere* atm, const frei_workspace* ws,
+                    double* d_k, double* d_sigma, void* stream);
+
+/* K2 (standalone).  propagate_fluxes() for one layer, elementwise over n
+ * wavelengths with g_0 = 0 (frei/twostream.py:97-177).  All arrays device
+ * doubles of length n; lam in cm. */
+int frei_b200_propagate(const double* d_lam_cm, const double* d_F1_up,
+                        const double* d_F2_down, double T1, double T2,
+                        const double* d_delta_tau, const double* d_omega0,
+                        double* d_F2_up, double* d_F1_down, int64_t n, void* stream);
+
+/* K2+K3.  One sweep over all layers and this device's wavelengths: the loop
+ * bodies of emit() (frei/twostream.py:356-405) or absorb() (:491-533) up to
+ * and including the four wavelength integrals, left as per-block partials.
+ * Requires layer_prep on the current T. */
+int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec,
+                    const frei_atmosphere* atm, const frei_flux* flux,
+                    int32_t direction, const frei_workspace* ws, void* stream);
+
+/* Deterministic fixed-order reduction of the block partials into ws->sums. */
+int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws,
+                     int64_t n_lam, void* stream);
+
+/* K4.  From ws->sums (after the cross-device sum when the wavelength axis is
+ * sharded): div_bol_net_flux, convective_flux, delta_t_i, delta_temperature
+ * (frei/twostream.py:23-43, 190-287) and T <- T - dT (:407, :536).
+ * alpha_override >= 0 replaces atm->alpha (the final emit of
+ * Grid.emission_spectrum does not forward alpha, frei/core.py:323-333).
+ * d_T_hist (nullable) receives the new T as one extra [B][L] record. */
+int frei_b200_update_T(const frei_atmosphere* atm, const frei_workspace* ws,
+                       int32_t direction, double alpha_override,
+                       double* d_T_hist, void* stream);
+
+/* Convenience for one device: layer_prep + sweep + reduce + update_T, i.e. one
+ * emit()/absorb() call of the reference with n_timesteps=1
+ * (frei/core.py:275-299). */
+int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec,
+                         const frei_atmosphere* atm, const frei_flux* flux,
+                         int32_t direction, double alpha_override,
+                         const frei_workspace* ws, double* d_T_hist, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FREI_B200_H */
