@@ -56,29 +56,30 @@ constexpr int kMaxS = 32;
 // ---------------------------------------------------------------------------
 // workspace layout
 // ---------------------------------------------------------------------------
-struct LayerParams {            // views into ws->layer_params
-    double*  dpg;               // [B][L]      (p1 - p2) / g
-    double*  invT;              // [B][L]      1 / T_i
-    double*  W;                 // [B][L][S][4] mmr-premultiplied corner weights
-    int32_t* base;              // [B][L][S]   table row of corner (iP, iT)
+// ws->layer_params holds one record of `rec8` 8-byte words per (atmosphere, level):
+//   [0] dpg = (p1 - p2) / g      [1] invT = 1 / T_i
+//   [2 + 4 s + c]  W[s][c]       mmr-premultiplied weight of corner c of species s
+//   [2 + 4 S + s]  off[s]        int64 element offset of table row (iP, iT) of species s
+// rec8 is even, so records and the W quadruples are 16-byte aligned: the sweep stages the
+// L records of its atmosphere into shared memory with one TMA bulk copy.
+struct LayerParams {
+    double* rec;                // [B][L][rec8]
+    int rec8;
+    int S;
 };
-
-static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
+__host__ __device__ static inline int rec_words(int S) { return (2 + 5 * S + 1) & ~1; }
 
 static inline int64_t layer_params_bytes(int B, int L, int S) {
-    return round16((int64_t)B * L * (16 + 36 * (int64_t)S));
+    return (int64_t)B * L * rec_words(S) * 8;
 }
-static inline LayerParams layer_params_view(void* p, int B, int L, int S) {
+static inline LayerParams layer_params_view(void* p, int S) {
     LayerParams v;
-    char* c = (char*)p;
-    int64_t n = (int64_t)B * L;
-    v.dpg = (double*)c;
-    v.invT = (double*)(c + n * 8);
-    v.W = (double*)(c + n * 16);
-    v.base = (int32_t*)(c + n * 16 + n * S * 32);
+    v.rec = (double*)p;
+    v.rec8 = rec_words(S);
+    v.S = S;
     return v;
 }
-static inline int64_t sweep_blocks(int64_t n_lam) { return (n_lam + kThreads - 1) / kThreads; }
+static inline int64_t sweep_blocks_max(int64_t n_lam) { return (n_lam + kThreads - 1) / kThreads; }
 
 // ---------------------------------------------------------------------------
 // K0: brackets, weights, per-layer scalars
@@ -101,6 +102,7 @@ struct PrepArgs {
     LayerParams lp;
     int32_t* iP; int32_t* iT; double* wP; double* wT; uint8_t* oob;
     int B, L, S, N_P, N_T;
+    int64_t n_lam;
 };
 
 __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
@@ -113,8 +115,9 @@ __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
     if (i == L - 1) p2 = p1 * (P[L - 2] * FREI_BAR) / (P[L - 3] * FREI_BAR);   // twostream.py:359
     else p2 = P[i + 1] * FREI_BAR;
     const int64_t li = (int64_t)b * L + i;
-    a.lp.dpg[li] = (p1 - p2) / g;                                              // twostream.py:231
-    a.lp.invT[li] = 1.0 / T[i];
+    double* rec = a.lp.rec + li * a.lp.rec8;
+    rec[0] = (p1 - p2) / g;                                                    // twostream.py:231
+    rec[1] = 1.0 / T[i];
     for (int s = 0; s < S; ++s) {
         const double* xp = a.axis_P + (int64_t)s * a.N_P;
         const double* xt = a.axis_T + (int64_t)s * a.N_T;
@@ -132,9 +135,10 @@ __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
         double w00 = (1.0 - wp) * (1.0 - wt), w01 = (1.0 - wp) * wt;
         double w10 = wp * (1.0 - wt), w11 = wp * wt;
         if (out) { w00 = w01 = w10 = w11 = 0.0; }       // fill_value=0, opacity.py:243
-        double* W = a.lp.W + (li * S + s) * 4;
+        double* W = rec + 2 + 4 * s;
         W[0] = m * w00; W[1] = m * w01; W[2] = m * w10; W[3] = m * w11;
-        a.lp.base[li * S + s] = (s * a.N_P + ip) * a.N_T + it;
+        reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s] =
+            (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
         if (a.iP) a.iP[li * S + s] = ip;
         if (a.iT) a.iT[li * S + s] = it;
         if (a.wP) a.wP[li * S + s] = wp;
@@ -187,28 +191,148 @@ __global__ void spectral_kernel(const double* __restrict__ lam_um, int64_t n_glo
 // ---------------------------------------------------------------------------
 // two-stream layer response, g_0 = 0   (twostream.py:139-176)
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ double planck(double c1, double c2, double invT) {
-    return c1 / expm1(c2 * invT);                        // twostream.py:64-67
+// ---- branch-free fp64 building blocks ---------------------------------------------------
+// The CUDA library's '/', sqrt(), exp() and expm1() each carry special-case branches and
+// call-outs that dominated the issue slots of the sweep (ncu, profiles/).  Arguments on this
+// path are finite, positive and far from the denormal range, so plain Newton refinement of the
+// hardware seeds is enough: results are within ~1 ulp (checked by tests through
+// frei_b200_debug_math).
+__device__ __forceinline__ double fast_rcp(double x) {
+    double y;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    double e = fma(-x, y, 1.0);
+    y = fma(y, e, y);
+    e = fma(-x, y, 1.0);
+    return fma(y, e, y);
 }
 
+// sqrt(x) and 1/sqrt(x) for normal positive x
+__device__ __forceinline__ double fast_sqrt(double x, double& rs) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+    const double hx = 0.5 * x;
+    double e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-hx * y, y, 0.5);
+    y = fma(y, e, y);
+    double g = x * y;
+    const double d = fma(-g, g, x);
+    g = fma(d, 0.5 * y, g);
+    rs = y;
+    return g;
+}
+
+// For u >= 0: T = exp(-u) and m = 1 - exp(-u), both to ~1 ulp (m without cancellation).
+// When the reduced argument needs no scaling (u < ln2/2, returned as `small`), uq = u Q(-u) =
+// 1 - m/u is also returned: it lets the caller form (T - 1)/u + 1 without cancellation.
+__device__ __forceinline__ void exp_neg(double u, double& T, double& m, double& uq, bool& small) {
+    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
+    u = fmin(u, 1400.0);                                 // exp(-1400) == 0 in fp64
+    const double tk = fma(-u, 1.4426950408889634, MAGIC);
+    const int ki = __double2loint(tk);                   // k = rint(-u / ln 2) <= 0
+    const double k = tk - MAGIC;
+    double s = fma(k, -6.93147180369123816490e-01, -u);  // ln2 hi
+    s = fma(k, -1.90821492927058770002e-10, s);          // ln2 lo;  |s| <= 0.3466
+    // expm1(s) = s + s^2 * Q(s), Q = sum_{n>=2} s^(n-2) / n!   (through s^13)
+    double q = 1.6059043836821613e-10;                   // 1/13!
+    q = fma(q, s, 2.08767569878681e-09);                 // 1/12!
+    q = fma(q, s, 2.505210838544172e-08);                // 1/11!
+    q = fma(q, s, 2.755731922398589e-07);                // 1/10!
+    q = fma(q, s, 2.7557319223985893e-06);               // 1/9!
+    q = fma(q, s, 2.48015873015873e-05);                 // 1/8!
+    q = fma(q, s, 1.984126984126984e-04);                // 1/7!
+    q = fma(q, s, 1.388888888888889e-03);                // 1/6!
+    q = fma(q, s, 8.333333333333333e-03);                // 1/5!
+    q = fma(q, s, 4.1666666666666664e-02);               // 1/4!
+    q = fma(q, s, 1.6666666666666666e-01);               // 1/3!
+    q = fma(q, s, 0.5);                                  // 1/2!
+    const double p = fma(s * s, q, s);                   // expm1(s)
+    const int ka = ki >> 1, kb = ki - ka;                // two-step scaling survives ki < -1022
+    const double s1 = __hiloint2double((ka + 1023) << 20, 0);
+    const double s2 = __hiloint2double((kb + 1023) << 20, 0);
+    T = (1.0 + p) * s1 * s2;
+    small = (ki == 0);
+    m = small ? -p : 1.0 - T;
+    uq = u * q;
+}
+__device__ __forceinline__ void exp_neg(double u, double& T, double& m) {
+    double uq; bool small;
+    exp_neg(u, T, m, uq, small);
+}
+
+__device__ __forceinline__ double planck(double c1, double c2, double invT) {
+    double e, m;                                         // c1 / expm1(x) = c1 e^-x / (1 - e^-x)
+    exp_neg(c2 * invT, e, m);                            // twostream.py:64-67
+    return c1 * e * fast_rcp(m);
+}
+
+// Algebraically identical to the reference's expressions (twostream.py:139-176), regrouped so
+// that no step subtracts nearly equal numbers.  With z = zeta_minus, m = 1 - T, u = -ln T:
+//   zeta_minus = (omega0 / E) / (2 (1 + r))          r = sqrt((E - omega0) / E)
+//   chi = -(r + z m)(1 - z m)     xi = (1 - z) z m (2 - m)     psi = -r T
+//   chi - psi - xi = -m (1 - z m) = -(xi + psi - chi)         B'/(2E) = (B1 - B2) r / u
+// The reference's own grouping loses up to ~4e-6 relative accuracy where delta_tau < 1e-6
+// ("conditioning"); this one tracks the exact value of the same formulas.
+// k = total opacity (includes sigma, opacity.py:269), sg = sigma, dpg = (p1 - p2)/g.
+__device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, double F1u, double F2d,
+                                             double B1, double B2, double& F2u, double& F1d,
+                                             double& dtau) {
+    dtau = dpg * k;                                                     // :371-373
+    const double R1 = fast_rcp(sg + k);
+    const double w0 = sg * R1, omw = k * R1;                            // omega0 (:376-378), 1 - omega0
+    double Ew = 1.0, invE = 1.0;
+    if (w0 > 0.1) {                                                     // :89-94
+        Ew = 1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0);
+        invE = fast_rcp(Ew);
+    }
+    const double EmW = Ew - w0;
+    double rs;
+    const double a = fast_sqrt(Ew * EmW, rs);
+    const double r = a * invE;                                          // sqrt((E - w0)/E), :143
+    const double u = 2.0 * a * dtau;                                    // T = exp(-u), :139
+    double Tr, m, uq;
+    bool small;
+    exp_neg(u, Tr, m, uq, small);
+    const double opr = 1.0 + r;
+    const double R2 = fast_rcp(opr * u);
+    const double z = 0.5 * (w0 * invE) * (u * R2);                      // zeta_minus, :145
+    const double e1 = small ? uq : fma(-(m * opr), R2, 1.0);            // 1 - m/u = (T - 1)/u + 1
+    const double zm = z * m, omzm = 1.0 - zm;
+    const double chi = -(r + zm) * omzm;                                // :149
+    const double xi = (1.0 - z) * zm * (2.0 - m);                       // :150
+    const double psi = -r * Tr;                                         // :151
+    const double A = fma(2.0, xi, -m * omzm);                           // chi + xi - psi
+    // T + ((T - 1)/u)(1 - z m) = (e1 - m) + z m (1 - e1): no O(1) terms cancel for small u
+    const double H = (B1 - B2) * r * fma(zm, 1.0 - e1, e1 - m);         // psi D + B'/(2E)(chi-psi-xi)
+    const double R3 = fast_rcp(EmW * chi);
+    const double ic = EmW * R3;                                         // 1 / chi
+    const double pc = (FREI_PI * omw) * R3;                             // pi (1 - w0)/(E - w0)/chi, :152
+    F2u = fma(ic, fma(psi, F1u, -xi * F2d), pc * fma(B2, A, H));        // :161-168
+    F1d = fma(ic, fma(psi, F2d, -xi * F1u), pc * fma(B1, A, -H));       // :169-176
+}
+
+// propagate_fluxes() signature: delta_tau and omega_0 given (twostream.py:97-99).
 __device__ __forceinline__ void two_stream(double dtau, double w0, double F1u, double F2d,
                                            double B1, double B2, double& F2u, double& F1d) {
-    const double Ew = (w0 > 0.1) ? (1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0)) : 1.0;   // :89-94
-    const double EmW = Ew - w0;
-    const double Tr = exp(-2.0 * sqrt(Ew * EmW) * dtau);                                // :139
-    const double r = sqrt(EmW / Ew);
-    const double zp = 0.5 * (1.0 + r), zm = 0.5 * (1.0 - r);                            // :143-146
-    const double Tr2 = Tr * Tr;
-    const double chi = zm * zm * Tr2 - zp * zp;                                         // :149
-    const double xi = zp * zm * (1.0 - Tr2);                                            // :150
-    const double psi = (zm * zm - zp * zp) * Tr;                                        // :151
-    const double pit = FREI_PI * (1.0 - w0) / EmW;                                      // :152
-    const double q = ((B1 - B2) / dtau) / (2.0 * Ew);                                   // :158, :165
-    const double inv_chi = 1.0 / chi;
-    F2u = inv_chi * (psi * F1u - xi * F2d +
-                     pit * (B2 * (chi + xi) - psi * B1 + q * (chi - psi - xi)));        // :161-168
-    F1d = inv_chi * (psi * F2d - xi * F1u +
-                     pit * (B1 * (chi + xi) - psi * B2 + q * (xi + psi - chi)));        // :169-176
+    // any (k, sigma, dpg) with sigma/(sigma+k) = w0 and dpg*k = dtau reproduces the inputs
+    double unused;
+    two_stream_k(1.0 - w0, w0, dtau / (1.0 - w0), F1u, F2d, B1, B2, F2u, F1d, unused);
+}
+
+// ---------------------------------------------------------------------------
+// debug: expose the fp64 building blocks for accuracy tests
+// ---------------------------------------------------------------------------
+__global__ void debug_math_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
+    const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double v = x[j];
+    double rs, T, m;
+    out[j] = fast_rcp(v);
+    out[n + j] = fast_sqrt(v, rs);
+    out[2 * n + j] = rs;
+    exp_neg(v, T, m);
+    out[3 * n + j] = T;
+    out[4 * n + j] = m;
 }
 
 // ---------------------------------------------------------------------------
@@ -225,9 +349,10 @@ __global__ void kappa_kernel(const TabT* __restrict__ tab, const double* __restr
     const int64_t li = (int64_t)b * L + i;
     const double sg = sigma[j] * (sigma_scale ? sigma_scale[b] : 1.0);
     double acc = 0.0;
+    const double* rec = lp.rec + li * lp.rec8;
     for (int s = 0; s < S; ++s) {
-        const double* W = lp.W + (li * S + s) * 4;
-        const TabT* r0 = tab + (int64_t)lp.base[li * S + s] * n_lam + j;
+        const double* W = rec + 2 + 4 * s;
+        const TabT* r0 = tab + reinterpret_cast<const int64_t*>(rec)[2 + 4 * S + s] + j;
         double v = 0.0;
         v += (double)r0[0] * W[0];
         v += (double)r0[n_lam] * W[1];
@@ -266,7 +391,7 @@ struct SweepArgs {
     const double* sigma_scale; const double* ftoa_scale;
     LayerParams lp;
     void* F_up; void* F_down; void* dtaus;
-    double* partials;           // [B][nblk][L][4]
+    double* partials;           // [B][gridDim.x][L][4]
     int64_t n_lam;
     int B, L, S, N_T;
 };
@@ -275,13 +400,11 @@ struct SweepArgs {
 // totals of v0, v1, v2, v3 respectively.  Fixed butterfly -> deterministic.
 __device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, double v3, int lane) {
     const unsigned full = 0xffffffffu;
-    // step 1 (xor 16): lower half keeps (v0, v1), upper half keeps (v2, v3)
     const bool up16 = lane & 16;
     double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;     // what I send
     double k0 = up16 ? v2 : v0, k1 = up16 ? v3 : v1;     // what I keep
     k0 += __shfl_xor_sync(full, s0, 16);
     k1 += __shfl_xor_sync(full, s1, 16);
-    // step 2 (xor 8): within each half, lanes with bit 3 clear keep k0, set keep k1
     const bool up8 = lane & 8;
     double s = up8 ? k0 : k1, k = up8 ? k1 : k0;
     k += __shfl_xor_sync(full, s, 8);
@@ -291,111 +414,237 @@ __device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, 
     return k;     // lane 0: v0, lane 8: v1, lane 16: v2, lane 24: v3
 }
 
-template <typename TabT, int S_T>
-__device__ __forceinline__ double gather_k(const TabT* __restrict__ tab, const LayerParams& lp,
-                                           int64_t li, int S, int N_T, int64_t n_lam, int64_t j) {
+// V consecutive wavelengths with one (vectorised when V == 2) load/store
+template <int V> struct Vec;
+template <> struct Vec<1> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) { o[0] = *p; }
+    static __device__ __forceinline__ void ldg(const double* p, double* o) { o[0] = __ldg(p); }
+    static __device__ __forceinline__ void ldg(const float* p, double* o) { o[0] = (double)__ldg(p); }
+    static __device__ __forceinline__ void st(double* p, const double* v) { *p = v[0]; }
+};
+template <> struct Vec<2> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) {
+        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
+    }
+    static __device__ __forceinline__ void ldg(const double* p, double* o) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
+    }
+    static __device__ __forceinline__ void ldg(const float* p, double* o) {
+        const float2 t = __ldg(reinterpret_cast<const float2*>(p)); o[0] = (double)t.x; o[1] = (double)t.y;
+    }
+    static __device__ __forceinline__ void st(double* p, const double* v) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+    }
+};
+
+// sum_s sum_corners W * table for V wavelengths: tabj = table + j; `rec` = this level's record
+// (shared memory); the four corners of a cell are rows r, r+1, r+N_T, r+N_T+1.
+template <typename TabT, int S_T, int V>
+__device__ __forceinline__ void gather_k(const TabT* __restrict__ tabj, const double* rec, int S,
+                                         int64_t n_lam, int64_t rowT, double* acc) {
     const int SS = (S_T > 0) ? S_T : S;
-    double acc = 0.0;
+    const int64_t* off = reinterpret_cast<const int64_t*>(rec) + 2 + 4 * SS;
+#pragma unroll
+    for (int v = 0; v < V; ++v) acc[v] = 0.0;
     if (S_T > 0) {
-        TabT t[S_T > 0 ? S_T : 1][4];
+        double t[S_T > 0 ? S_T : 1][4][V];
 #pragma unroll
         for (int s = 0; s < SS; ++s) {
-            const TabT* r0 = tab + (int64_t)__ldg(lp.base + li * SS + s) * n_lam + j;
-            t[s][0] = __ldg(r0);
-            t[s][1] = __ldg(r0 + n_lam);
-            t[s][2] = __ldg(r0 + (int64_t)N_T * n_lam);
-            t[s][3] = __ldg(r0 + (int64_t)(N_T + 1) * n_lam);
+            const TabT* r0 = tabj + off[s];
+            Vec<V>::ldg(r0, t[s][0]);
+            Vec<V>::ldg(r0 + n_lam, t[s][1]);
+            Vec<V>::ldg(r0 + rowT, t[s][2]);
+            Vec<V>::ldg(r0 + rowT + n_lam, t[s][3]);
         }
 #pragma unroll
         for (int s = 0; s < SS; ++s) {
-            const double4* Wp = reinterpret_cast<const double4*>(lp.W + (li * SS + s) * 4);
-            const double2 wa = __ldg(reinterpret_cast<const double2*>(Wp));
-            const double2 wb = __ldg(reinterpret_cast<const double2*>(Wp) + 1);
-            double v = (double)t[s][0] * wa.x;
-            v = fma((double)t[s][1], wa.y, v);
-            v = fma((double)t[s][2], wb.x, v);
-            v = fma((double)t[s][3], wb.y, v);
-            acc += v;
+            const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
+            const double2 wb = *reinterpret_cast<const double2*>(rec + 4 + 4 * s);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double x = t[s][0][v] * wa.x;
+                x = fma(t[s][1][v], wa.y, x);
+                x = fma(t[s][2][v], wb.x, x);
+                x = fma(t[s][3][v], wb.y, x);
+                acc[v] += x;
+            }
         }
     } else {
         for (int s = 0; s < SS; ++s) {
-            const TabT* r0 = tab + (int64_t)__ldg(lp.base + li * SS + s) * n_lam + j;
-            const double* W = lp.W + (li * SS + s) * 4;
-            double v = (double)__ldg(r0) * __ldg(W);
-            v = fma((double)__ldg(r0 + n_lam), __ldg(W + 1), v);
-            v = fma((double)__ldg(r0 + (int64_t)N_T * n_lam), __ldg(W + 2), v);
-            v = fma((double)__ldg(r0 + (int64_t)(N_T + 1) * n_lam), __ldg(W + 3), v);
-            acc += v;
+            const TabT* r0 = tabj + off[s];
+            const double* W = rec + 2 + 4 * s;
+            double t0[V], t1[V], t2[V], t3[V];
+            Vec<V>::ldg(r0, t0);
+            Vec<V>::ldg(r0 + n_lam, t1);
+            Vec<V>::ldg(r0 + rowT, t2);
+            Vec<V>::ldg(r0 + rowT + n_lam, t3);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                double x = t0[v] * W[0];
+                x = fma(t1[v], W[1], x);
+                x = fma(t2[v], W[2], x);
+                x = fma(t3[v], W[3], x);
+                acc[v] += x;
+            }
         }
     }
-    return acc;
 }
 
-template <typename TabT, int S_T, int DIR>
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// One CTA = kThreads * V consecutive wavelengths of one atmosphere, all layers.  Each thread
+// carries the running stream (F_up for emit, F_down for absorb) and the Planck term of the
+// shared level in registers; the other stream is read stale from HBM and both are written
+// back.  The level records are staged into shared memory by one TMA bulk copy.
+template <typename TabT, int S_T, int DIR, int V>
 __global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
-    extern __shared__ double sm_part[];          // [L][kWarps][4]
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
-    const int L = a.L, S = a.S;
+    const int L = a.L, S = a.S, rec8 = a.lp.rec8;
+    double* sm_rec = smem;                       // [L][rec8]
+    double* sm_part = smem + (size_t)L * rec8;   // [L][kWarps][4]
     const int64_t n_lam = a.n_lam;
-    const int64_t j_raw = (int64_t)blockIdx.x * kThreads + tid;
-    const bool live = j_raw < n_lam;
-    const int64_t j = live ? j_raw : n_lam - 1;
 
-    const TabT* tab = static_cast<const TabT*>(a.tab);
+    // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
+    const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double* src = a.lp.rec + (int64_t)b * L * rec8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+
+    // ---- per-wavelength constants (overlaps the copy) ----
+    const int64_t j_raw = ((int64_t)blockIdx.x * kThreads + tid) * V;
+    const bool live = j_raw < n_lam;             // n_lam % V == 0, so all V lanes are in range
+    const int64_t j = live ? j_raw : n_lam - V;
+    const TabT* tabj = static_cast<const TabT*>(a.tab) + j;
+    const int64_t rowT = (int64_t)a.N_T * n_lam;
     double* Fu = static_cast<double*>(a.F_up) + (int64_t)b * L * n_lam + j;
     double* Fd = static_cast<double*>(a.F_down) + (int64_t)b * L * n_lam + j;
     double* dt_out = a.dtaus ? static_cast<double*>(a.dtaus) + (int64_t)b * L * n_lam + j : nullptr;
+    double c1[V], c2[V], sg[V], wj[V];
+    Vec<V>::ldg(a.c1 + j, c1);
+    Vec<V>::ldg(a.c2 + j, c2);
+    Vec<V>::ldg(a.sigma + j, sg);
+    Vec<V>::ldg(a.w + j, wj);
+    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) { sg[v] *= sscale; if (!live) wj[v] = 0.0; }
+    if (dt_out && live) {                        // leading row of ones, twostream.py:352/:487
+        double one[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) one[v] = 1.0;
+        Vec<V>::st(dt_out, one);
+    }
 
-    const double c1 = a.c1[j], c2 = a.c2[j];
-    const double sg = a.sigma[j] * (a.sigma_scale ? a.sigma_scale[b] : 1.0);
-    const double wj = live ? a.w[j] : 0.0;
-    const int64_t lb = (int64_t)b * L;
+    // ---- wait for the records ----
+    {
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        }
+    }
 
-    if (dt_out && live) dt_out[0] = 1.0;         // leading row of ones, twostream.py:352/:487
-
+    double Fcar[V], Bcar[V];                     // carried stream and carried Planck term
     if (DIR == FREI_EMIT) {
-        const double ftoa = a.f_toa[j] * (a.ftoa_scale ? a.ftoa_scale[b] : 1.0);
-        double F1u = Fu[n_lam];                                  // fluxes_up[1], stale
-        double B1 = planck(c1, c2, __ldg(a.lp.invT + lb + 1));
-        if (warp == 0 && lane < 4) sm_part[(0 * kWarps + 0) * 4 + lane] = 0.0;
+        double ftoa[V];
+        Vec<V>::ldg(a.f_toa + j, ftoa);
+        const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
+        Vec<V>::ld(Fu + n_lam, Fcar);                            // fluxes_up[1], stale
+        const double invT1 = sm_rec[rec8 + 1];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { ftoa[v] *= fscale; Bcar[v] = planck(c1[v], c2[v], invT1); }
+        const double* pFd = Fd + 2 * n_lam;                      // fluxes_down[i + 1]
+        double* pFu_out = Fu + 2 * n_lam;                        // fluxes_up[i + 1]
+        double* pFd_out = Fd + n_lam;                            // fluxes_down[i]
+        double* pdt = dt_out ? dt_out + n_lam : nullptr;
         for (int i = 1; i < L; ++i) {
             const bool top = (i == L - 1);
-            const double F2d = top ? ftoa : Fd[(int64_t)(i + 1) * n_lam];     // :379-382
-            const double k = gather_k<TabT, S_T>(tab, a.lp, lb + i, S, a.N_T, n_lam, j) + sg;
-            const double B2 = top ? B1 : planck(c1, c2, __ldg(a.lp.invT + lb + i + 1));
-            const double dtau = __ldg(a.lp.dpg + lb + i) * k;                 // :371-373
-            const double w0 = sg / (sg + k);                                  // :376-378
-            double F2u, F1d;
-            two_stream(dtau, w0, F1u, F2d, B1, B2, F2u, F1d);
-            if (live) {
-                if (!top) Fu[(int64_t)(i + 1) * n_lam] = F2u;                 // :392-394
-                Fd[(int64_t)i * n_lam] = F1d;
-                if (dt_out) dt_out[(int64_t)i * n_lam] = dtau;
+            const double* rec = sm_rec + (size_t)i * rec8;
+            double F2d[V], k[V];
+            if (top) {
+#pragma unroll
+                for (int v = 0; v < V; ++v) F2d[v] = ftoa[v];    // :379-382
+            } else {
+                Vec<V>::ld(pFd, F2d);
             }
-            const double red = warp_reduce4(wj * F2u, wj * F2d, wj * F1u, wj * F1d, lane);
-            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = red;
-            F1u = F2u; B1 = B2;
+            gather_k<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, k);
+            const double dpg = rec[0];
+            const double invT2 = top ? 0.0 : rec[rec8 + 1];
+            double F2u[V], F1d[V], dtau[V], red[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const double B2 = top ? Bcar[v] : planck(c1[v], c2[v], invT2);   // :358-363
+                two_stream_k(k[v] + sg[v], sg[v], dpg, Fcar[v], F2d[v], Bcar[v], B2,
+                             F2u[v], F1d[v], dtau[v]);
+                red[0] = fma(wj[v], F2u[v], red[0]);
+                red[1] = fma(wj[v], F2d[v], red[1]);
+                red[2] = fma(wj[v], Fcar[v], red[2]);
+                red[3] = fma(wj[v], F1d[v], red[3]);
+                Fcar[v] = F2u[v];
+                Bcar[v] = B2;
+            }
+            if (live) {
+                if (!top) Vec<V>::st(pFu_out, F2u);                           // :392-394
+                Vec<V>::st(pFd_out, F1d);
+                if (pdt) Vec<V>::st(pdt, dtau);
+            }
+            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
+            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = r4;
+            pFd += n_lam; pFu_out += n_lam; pFd_out += n_lam;
+            if (pdt) pdt += n_lam;
         }
     } else {
-        double F2d = Fd[(int64_t)(L - 1) * n_lam];                            // fluxes_down[L-1]
-        double B2 = planck(c1, c2, __ldg(a.lp.invT + lb + L - 1));
+        Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, Fcar);                      // fluxes_down[L-1]
+        const double invTt = sm_rec[(size_t)(L - 1) * rec8 + 1];
+#pragma unroll
+        for (int v = 0; v < V; ++v) Bcar[v] = planck(c1[v], c2[v], invTt);
+        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;                    // fluxes_up[i], stale
+        double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                      // fluxes_up[i + 1]
+        double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                      // fluxes_down[i]
+        double* pdt = dt_out ? dt_out + n_lam : nullptr;                      // visiting order
         for (int i = L - 2; i >= 0; --i) {
-            const double F1u = Fu[(int64_t)i * n_lam];                        // stale, :512
-            const double k = gather_k<TabT, S_T>(tab, a.lp, lb + i, S, a.N_T, n_lam, j) + sg;
-            const double B1 = planck(c1, c2, __ldg(a.lp.invT + lb + i));
-            const double dtau = __ldg(a.lp.dpg + lb + i) * k;
-            const double w0 = sg / (sg + k);
-            double F2u, F1d;
-            two_stream(dtau, w0, F1u, F2d, B1, B2, F2u, F1d);
-            if (live) {
-                Fu[(int64_t)(i + 1) * n_lam] = F2u;                           // :521-522
-                Fd[(int64_t)i * n_lam] = F1d;
-                if (dt_out) dt_out[(int64_t)(L - 1 - i) * n_lam] = dtau;      // visiting order
+            const double* rec = sm_rec + (size_t)i * rec8;
+            double F1u[V], k[V];
+            Vec<V>::ld(pFu, F1u);                                             // :512
+            gather_k<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, k);
+            const double dpg = rec[0], invT1 = rec[1];
+            double F2u[V], F1d[V], dtau[V], red[4] = {0.0, 0.0, 0.0, 0.0};
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                const double B1 = planck(c1[v], c2[v], invT1);
+                two_stream_k(k[v] + sg[v], sg[v], dpg, F1u[v], Fcar[v], B1, Bcar[v],
+                             F2u[v], F1d[v], dtau[v]);
+                red[0] = fma(wj[v], F2u[v], red[0]);
+                red[1] = fma(wj[v], Fcar[v], red[1]);
+                red[2] = fma(wj[v], F1u[v], red[2]);
+                red[3] = fma(wj[v], F1d[v], red[3]);
+                Fcar[v] = F1d[v];
+                Bcar[v] = B1;
             }
-            const double red = warp_reduce4(wj * F2u, wj * F2d, wj * F1u, wj * F1d, lane);
-            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = red;
-            F2d = F1d; B2 = B1;
+            if (live) {
+                Vec<V>::st(pFu_out, F2u);                                     // :521-522
+                Vec<V>::st(pFd_out, F1d);
+                if (pdt) Vec<V>::st(pdt, dtau);
+            }
+            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
+            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = r4;
+            pFu -= n_lam; pFu_out -= n_lam; pFd_out -= n_lam;
+            if (pdt) pdt += n_lam;
         }
     }
     __syncthreads();
@@ -491,30 +740,39 @@ __global__ void update_T_kernel(double* __restrict__ T, const double* __restrict
 // ---------------------------------------------------------------------------
 // host side of the ABI
 // ---------------------------------------------------------------------------
-template <typename TabT, int S_T>
-static int launch_sweep_dir(const SweepArgs& a, int direction, dim3 grid, size_t smem, cudaStream_t st) {
-    if (direction == FREI_EMIT) {
-        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, FREI_EMIT>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sweep_kernel<TabT, S_T, FREI_EMIT><<<grid, kThreads, smem, st>>>(a);
-    } else {
-        CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, FREI_ABSORB>,
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        sweep_kernel<TabT, S_T, FREI_ABSORB><<<grid, kThreads, smem, st>>>(a);
-    }
+static inline int sweep_V(int64_t n_lam) { return (n_lam % 2 == 0) ? 2 : 1; }
+static inline int64_t sweep_blocks(int64_t n_lam) {
+    const int64_t per = (int64_t)kThreads * sweep_V(n_lam);
+    return (n_lam + per - 1) / per;
+}
+
+template <typename TabT, int S_T, int DIR, int V>
+static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V>,
+                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    sweep_kernel<TabT, S_T, DIR, V><<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
 
+template <typename TabT, int S_T>
+static int launch_sweep_dir(const SweepArgs& a, int direction, int V, dim3 grid, size_t smem,
+                            cudaStream_t st) {
+    if (direction == FREI_EMIT)
+        return V == 2 ? launch_sweep_one<TabT, S_T, FREI_EMIT, 2>(a, grid, smem, st)
+                      : launch_sweep_one<TabT, S_T, FREI_EMIT, 1>(a, grid, smem, st);
+    return V == 2 ? launch_sweep_one<TabT, S_T, FREI_ABSORB, 2>(a, grid, smem, st)
+                  : launch_sweep_one<TabT, S_T, FREI_ABSORB, 1>(a, grid, smem, st);
+}
+
 template <typename TabT>
-static int launch_sweep(const SweepArgs& a, int direction, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch_sweep(const SweepArgs& a, int direction, int V, dim3 grid, size_t smem,
+                        cudaStream_t st) {
     switch (a.S) {
-        case 1: return launch_sweep_dir<TabT, 1>(a, direction, grid, smem, st);
-        case 2: return launch_sweep_dir<TabT, 2>(a, direction, grid, smem, st);
-        case 3: return launch_sweep_dir<TabT, 3>(a, direction, grid, smem, st);
-        case 4: return launch_sweep_dir<TabT, 4>(a, direction, grid, smem, st);
-        case 8: return launch_sweep_dir<TabT, 8>(a, direction, grid, smem, st);
-        default: return launch_sweep_dir<TabT, 0>(a, direction, grid, smem, st);
+        case 1: return launch_sweep_dir<TabT, 1>(a, direction, V, grid, smem, st);
+        case 3: return launch_sweep_dir<TabT, 3>(a, direction, V, grid, smem, st);
+        case 8: return launch_sweep_dir<TabT, 8>(a, direction, V, grid, smem, st);
+        default: return launch_sweep_dir<TabT, 0>(a, direction, V, grid, smem, st);
     }
 }
 
@@ -533,7 +791,7 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
                               int64_t* layer_params, int64_t* partials, int64_t* sums, int64_t* dT) {
     ARG_TRY(B > 0 && L >= 3 && S > 0 && S <= kMaxS && n_lam > 0);
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
-    if (partials) *partials = (int64_t)B * sweep_blocks(n_lam) * L * 4 * 8;
+    if (partials) *partials = (int64_t)B * sweep_blocks_max(n_lam) * L * 4 * 8;
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -564,6 +822,13 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
     return FREI_OK;
 }
 
+int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream) {
+    ARG_TRY(d_x && d_out && n > 0);
+    debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n);
+    CUDA_TRY(cudaGetLastError());
+    return FREI_OK;
+}
+
 int frei_b200_layer_prep(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
                          int32_t* d_iP, int32_t* d_iT, double* d_wP, double* d_wT, uint8_t* d_oob,
                          void* stream) {
@@ -572,9 +837,10 @@ int frei_b200_layer_prep(const frei_table* tab, const frei_atmosphere* atm, cons
     PrepArgs a;
     a.axis_P = tab->axis_P; a.axis_T = tab->axis_T; a.has_T = tab->has_T;
     a.T = atm->T; a.P = atm->P; a.mmr = atm->mmr; a.g = atm->g;
-    a.lp = layer_params_view(ws->layer_params, atm->B, atm->L, tab->S);
+    a.lp = layer_params_view(ws->layer_params, tab->S);
     a.iP = d_iP; a.iT = d_iT; a.wP = d_wP; a.wT = d_wT; a.oob = d_oob;
     a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_P = tab->N_P; a.N_T = tab->N_T;
+    a.n_lam = tab->n_lam;
     const int n = atm->B * atm->L;
     prep_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
     CUDA_TRY(cudaGetLastError());
@@ -587,7 +853,7 @@ int frei_b200_kappa(const frei_table* tab, const frei_spectral* spec, const frei
     if (rc) return rc;
     ARG_TRY(spec && spec->sigma && d_k && d_sigma && spec->n_lam == tab->n_lam);
     ARG_TRY(atm->L <= 65535 && atm->B <= 65535);
-    LayerParams lp = layer_params_view(ws->layer_params, atm->B, atm->L, tab->S);
+    LayerParams lp = layer_params_view(ws->layer_params, tab->S);
     dim3 grid((unsigned)((tab->n_lam + 255) / 256), atm->L, atm->B);
     if (tab->dtype == FREI_F32)
         kappa_kernel<float><<<grid, 256, 0, (cudaStream_t)stream>>>(
@@ -627,15 +893,17 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.tab = tab->values;
     a.c1 = spec->c1; a.c2 = spec->c2; a.sigma = spec->sigma; a.w = spec->w; a.f_toa = spec->f_toa;
     a.sigma_scale = atm->sigma_scale; a.ftoa_scale = atm->ftoa_scale;
-    a.lp = layer_params_view(ws->layer_params, atm->B, atm->L, tab->S);
+    a.lp = layer_params_view(ws->layer_params, tab->S);
     a.F_up = flux->F_up; a.F_down = flux->F_down; a.dtaus = flux->dtaus;
     a.partials = ws->partials;
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
+    const int V = sweep_V(tab->n_lam);
     dim3 grid((unsigned)sweep_blocks(tab->n_lam), atm->B);
-    const size_t smem = (size_t)atm->L * kWarps * 4 * sizeof(double);
-    if (smem > 200 * 1024) return set_err(FREI_E_UNSUPPORTED, "too many layers for shared memory%s%s");
-    if (tab->dtype == FREI_F32) return launch_sweep<float>(a, direction, grid, smem, (cudaStream_t)stream);
-    return launch_sweep<double>(a, direction, grid, smem, (cudaStream_t)stream);
+    const size_t smem = ((size_t)atm->L * a.lp.rec8 + (size_t)atm->L * kWarps * 4) * sizeof(double);
+    if (smem > 200 * 1024)
+        return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
+    if (tab->dtype == FREI_F32) return launch_sweep<float>(a, direction, V, grid, smem, (cudaStream_t)stream);
+    return launch_sweep<double>(a, direction, V, grid, smem, (cudaStream_t)stream);
 }
 
 int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws, int64_t n_lam, void* stream) {

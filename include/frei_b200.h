@@ -129,6 +129,10 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
                              double f, double* d_c1, double* d_c2, double* d_sigma,
                              double* d_w, double* d_f_toa, void* stream);
 
+/* Test hook: for n positive inputs x writes out[0..5n) = 1/x, sqrt(x), 1/sqrt(x),
+ * exp(-x), 1 - exp(-x) as computed by the kernels' branch-free fp64 routines. */
+int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream);
+
 /* K0.  Bracket (P_i, T_i) of every level in every species' axes with the rule
  * of scipy.interpolate's find_indices (reached from frei/opacity.py:261-263),
  * build mmr-premultiplied corner weights (zero when out of bounds:
