@@ -23,6 +23,11 @@ NVCC_FLAGS = [
 ]
 
 
+def _extra_flags():
+    """Experiment knobs, e.g. FREI_B200_NVCC_EXTRA='-DSWEEP_MINB=6 -DSWEEP_THREADS=64'."""
+    return os.environ.get('FREI_B200_NVCC_EXTRA', '').split()
+
+
 def lib_path():
     return os.path.join(LIBDIR, LIBNAME)
 
@@ -39,7 +44,7 @@ def _digest():
     for f in files:
         with open(f, 'rb') as fh:
             hsh.update(fh.read())
-    hsh.update(' '.join(NVCC_FLAGS).encode())
+    hsh.update(' '.join(NVCC_FLAGS + _extra_flags()).encode())
     return hsh.hexdigest()
 
 
@@ -59,7 +64,7 @@ def build(force=False, verbose=False):
     nvcc = find_nvcc()
     if nvcc is None:
         raise RuntimeError('nvcc not found: cannot build libfrei_b200.so')
-    cmd = [nvcc] + NVCC_FLAGS + ['-I', INCLUDE, '-o', lib_path()] + _sources()
+    cmd = [nvcc] + NVCC_FLAGS + _extra_flags() + ['-I', INCLUDE, '-o', lib_path()] + _sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     log = res.stdout + res.stderr
     with open(os.path.join(LIBDIR, 'build.log'), 'w') as fh:

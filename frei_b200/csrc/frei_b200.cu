@@ -49,7 +49,13 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
 #define FREI_BAR     1e6
 #define FREI_PI      3.141592653589793
 
-constexpr int kThreads = 128;            // threads per sweep CTA (4 warps)
+#ifndef SWEEP_THREADS
+#define SWEEP_THREADS 128
+#endif
+#ifndef SWEEP_MINB
+#define SWEEP_MINB 4
+#endif
+constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxS = 32;
 
@@ -79,7 +85,7 @@ static inline LayerParams layer_params_view(void* p, int S) {
     v.S = S;
     return v;
 }
-static inline int64_t sweep_blocks_max(int64_t n_lam) { return (n_lam + kThreads - 1) / kThreads; }
+static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + kWarps; }   // warps at V = 1
 
 // ---------------------------------------------------------------------------
 // K0: brackets, weights, per-layer scalars
@@ -233,24 +239,22 @@ __device__ __forceinline__ void exp_neg(double u, double& T, double& m, double& 
     const double k = tk - MAGIC;
     double s = fma(k, -6.93147180369123816490e-01, -u);  // ln2 hi
     s = fma(k, -1.90821492927058770002e-10, s);          // ln2 lo;  |s| <= 0.3466
-    // expm1(s) = s + s^2 * Q(s), Q = sum_{n>=2} s^(n-2) / n!   (through s^13)
-    double q = 1.6059043836821613e-10;                   // 1/13!
-    q = fma(q, s, 2.08767569878681e-09);                 // 1/12!
-    q = fma(q, s, 2.505210838544172e-08);                // 1/11!
-    q = fma(q, s, 2.755731922398589e-07);                // 1/10!
-    q = fma(q, s, 2.7557319223985893e-06);               // 1/9!
-    q = fma(q, s, 2.48015873015873e-05);                 // 1/8!
-    q = fma(q, s, 1.984126984126984e-04);                // 1/7!
-    q = fma(q, s, 1.388888888888889e-03);                // 1/6!
-    q = fma(q, s, 8.333333333333333e-03);                // 1/5!
-    q = fma(q, s, 4.1666666666666664e-02);               // 1/4!
-    q = fma(q, s, 1.6666666666666666e-01);               // 1/3!
-    q = fma(q, s, 0.5);                                  // 1/2!
-    const double p = fma(s * s, q, s);                   // expm1(s)
+    // expm1(s) = s + s^2 Q(s), Q = sum_{n>=2} s^(n-2) / n! through s^13, evaluated with Estrin's
+    // scheme (dependency depth 4 instead of 12: the sweep is bound by fp64 latency chains)
+    const double s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
+    const double a0 = fma(1.6666666666666666e-01, s, 0.5);                       // 1/3!, 1/2!
+    const double a1 = fma(8.333333333333333e-03, s, 4.1666666666666664e-02);     // 1/5!, 1/4!
+    const double a2 = fma(1.984126984126984e-04, s, 1.388888888888889e-03);      // 1/7!, 1/6!
+    const double a3 = fma(2.7557319223985893e-06, s, 2.48015873015873e-05);      // 1/9!, 1/8!
+    const double a4 = fma(2.505210838544172e-08, s, 2.755731922398589e-07);      // 1/11!, 1/10!
+    const double a5 = fma(1.6059043836821613e-10, s, 2.08767569878681e-09);      // 1/13!, 1/12!
+    const double b0 = fma(a1, s2, a0), b1 = fma(a3, s2, a2), b2 = fma(a5, s2, a4);
+    const double q = fma(b2, s8, fma(b1, s4, b0));
+    const double p = fma(s2, q, s);                      // expm1(s)
     const int ka = ki >> 1, kb = ki - ka;                // two-step scaling survives ki < -1022
-    const double s1 = __hiloint2double((ka + 1023) << 20, 0);
-    const double s2 = __hiloint2double((kb + 1023) << 20, 0);
-    T = (1.0 + p) * s1 * s2;
+    const double sc1 = __hiloint2double((ka + 1023) << 20, 0);
+    const double sc2 = __hiloint2double((kb + 1023) << 20, 0);
+    T = (1.0 + p) * sc1 * sc2;
     small = (ki == 0);
     m = small ? -p : 1.0 - T;
     uq = u * q;
@@ -280,11 +284,12 @@ __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, do
     dtau = dpg * k;                                                     // :371-373
     const double R1 = fast_rcp(sg + k);
     const double w0 = sg * R1, omw = k * R1;                            // omega0 (:376-378), 1 - omega0
-    double Ew = 1.0, invE = 1.0;
-    if (w0 > 0.1) {                                                     // :89-94
-        Ew = 1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0);
-        invE = fast_rcp(Ew);
-    }
+    // Deitrick (2020) Eqn 19 with g_0 = 0 (:89-94), select instead of branch so the whole
+    // layer step stays one basic block for the instruction scheduler
+    const bool hi = w0 > 0.1;
+    const double Ep = 1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0);
+    const double Ew = hi ? Ep : 1.0;
+    const double invE = hi ? fast_rcp(Ep) : 1.0;
     const double EmW = Ew - w0;
     double rs;
     const double a = fast_sqrt(Ew * EmW, rs);
@@ -391,7 +396,7 @@ struct SweepArgs {
     const double* sigma_scale; const double* ftoa_scale;
     LayerParams lp;
     void* F_up; void* F_down; void* dtaus;
-    double* partials;           // [B][gridDim.x][L][4]
+    double* partials;           // [B][gridDim.x * kWarps][L][4]
     int64_t n_lam;
     int B, L, S, N_T;
 };
@@ -437,76 +442,141 @@ template <> struct Vec<2> {
     }
 };
 
-// sum_s sum_corners W * table for V wavelengths: tabj = table + j; `rec` = this level's record
-// (shared memory); the four corners of a cell are rows r, r+1, r+N_T, r+N_T+1.
+// ---- opacity rows: asynchronous staging into shared memory (cp.async) ------------------------
+// Every thread copies the 4 S table elements (x V wavelengths) of the NEXT level into its own
+// slots while it computes the current level, then folds them into k.  The slots of a thread are
+// private to it, so no CTA barrier is involved — only cp.async.wait_group.
+template <int BYTES>
+__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// slot of (species s, corner c) for this thread: stage + (4 s + c) * kRowBytes
 template <typename TabT, int S_T, int V>
-__device__ __forceinline__ void gather_k(const TabT* __restrict__ tabj, const double* rec, int S,
-                                         int64_t n_lam, int64_t rowT, double* acc) {
+__device__ __forceinline__ void stage_rows(const TabT* __restrict__ tabj, const double* rec, int S,
+                                           int64_t n_lam, int64_t rowT, uint32_t stage) {
     const int SS = (S_T > 0) ? S_T : S;
+    constexpr int kSlot = V * (int)sizeof(TabT);
+    constexpr uint32_t kRow = (uint32_t)kThreads * kSlot;
     const int64_t* off = reinterpret_cast<const int64_t*>(rec) + 2 + 4 * SS;
 #pragma unroll
-    for (int v = 0; v < V; ++v) acc[v] = 0.0;
-    if (S_T > 0) {
-        double t[S_T > 0 ? S_T : 1][4][V];
+    for (int s = 0; s < SS; ++s) {
+        const TabT* r0 = tabj + off[s];
+        cp_async<kSlot>(stage + (4 * s + 0) * kRow, r0);
+        cp_async<kSlot>(stage + (4 * s + 1) * kRow, r0 + n_lam);
+        cp_async<kSlot>(stage + (4 * s + 2) * kRow, r0 + rowT);
+        cp_async<kSlot>(stage + (4 * s + 3) * kRow, r0 + rowT + n_lam);
+    }
+    cp_async_commit();
+}
+
+template <int V> struct SVec;
+template <> struct SVec<1> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) { o[0] = *p; }
+    static __device__ __forceinline__ void ld(const float* p, double* o) { o[0] = (double)*p; }
+};
+template <> struct SVec<2> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) {
+        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
+    }
+    static __device__ __forceinline__ void ld(const float* p, double* o) {
+        const float2 t = *reinterpret_cast<const float2*>(p); o[0] = (double)t.x; o[1] = (double)t.y;
+    }
+};
+
+// k[v] = sigma + sum_s sum_corners W[s][c] * staged[s][c][v]   (opacity.py:261-269)
+template <typename TabT, int S_T, int V>
+__device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec, int S,
+                                            const double* sg, double* k) {
+    const int SS = (S_T > 0) ? S_T : S;
+    constexpr int kRowElems = kThreads * V;
 #pragma unroll
-        for (int s = 0; s < SS; ++s) {
-            const TabT* r0 = tabj + off[s];
-            Vec<V>::ldg(r0, t[s][0]);
-            Vec<V>::ldg(r0 + n_lam, t[s][1]);
-            Vec<V>::ldg(r0 + rowT, t[s][2]);
-            Vec<V>::ldg(r0 + rowT + n_lam, t[s][3]);
-        }
+    for (int v = 0; v < V; ++v) k[v] = 0.0;
+#pragma unroll 4
+    for (int s = 0; s < SS; ++s) {
+        const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
+        const double2 wb = *reinterpret_cast<const double2*>(rec + 4 + 4 * s);
+        double t0[V], t1[V], t2[V], t3[V];
+        SVec<V>::ld(slot + (4 * s + 0) * kRowElems, t0);
+        SVec<V>::ld(slot + (4 * s + 1) * kRowElems, t1);
+        SVec<V>::ld(slot + (4 * s + 2) * kRowElems, t2);
+        SVec<V>::ld(slot + (4 * s + 3) * kRowElems, t3);
 #pragma unroll
-        for (int s = 0; s < SS; ++s) {
-            const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
-            const double2 wb = *reinterpret_cast<const double2*>(rec + 4 + 4 * s);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                double x = t[s][0][v] * wa.x;
-                x = fma(t[s][1][v], wa.y, x);
-                x = fma(t[s][2][v], wb.x, x);
-                x = fma(t[s][3][v], wb.y, x);
-                acc[v] += x;
-            }
-        }
-    } else {
-        for (int s = 0; s < SS; ++s) {
-            const TabT* r0 = tabj + off[s];
-            const double* W = rec + 2 + 4 * s;
-            double t0[V], t1[V], t2[V], t3[V];
-            Vec<V>::ldg(r0, t0);
-            Vec<V>::ldg(r0 + n_lam, t1);
-            Vec<V>::ldg(r0 + rowT, t2);
-            Vec<V>::ldg(r0 + rowT + n_lam, t3);
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                double x = t0[v] * W[0];
-                x = fma(t1[v], W[1], x);
-                x = fma(t2[v], W[2], x);
-                x = fma(t3[v], W[3], x);
-                acc[v] += x;
-            }
+        for (int v = 0; v < V; ++v) {
+            double x = t0[v] * wa.x;
+            x = fma(t1[v], wa.y, x);
+            x = fma(t2[v], wb.x, x);
+            x = fma(t3[v], wb.y, x);
+            k[v] += x;
         }
     }
+#pragma unroll
+    for (int v = 0; v < V; ++v) k[v] += sg[v];            // k includes sigma, opacity.py:269
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Per-thread state of the sweep: V wavelengths.
+template <int V>
+struct Lane {
+    double c1[V], c2[V], sg[V], wj[V];
+    double Fcar[V], Bcar[V];     // carried stream (F_up for emit, F_down for absorb) and Planck term
+};
+
+// One layer-step for V wavelengths.  `other` = the stale stream entering the layer, `invTn` =
+// 1/T of the level whose Planck term is new this step (ignored when SAME_T: emit's top
+// pseudo-layer has T_2 = T_1, twostream.py:358-363).  Writes the two outgoing streams, the four
+// wavelength-integral contributions of this warp, and optionally delta_tau.
+template <int DIR, int V, bool SAME_T>
+__device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double dpg, const double* other,
+                                           double invTn, double* F2u, double* F1d, double* dtau,
+                                           double* red) {
+    red[0] = red[1] = red[2] = red[3] = 0.0;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn);
+        if (DIR == FREI_EMIT) {          // carried = F_1_up, B_1; other = F_2_down; new B = B_2
+            two_stream_k(k[v], t.sg[v], dpg, t.Fcar[v], other[v], t.Bcar[v], Bn,
+                         F2u[v], F1d[v], dtau[v]);
+            red[0] = fma(t.wj[v], F2u[v], red[0]);
+            red[1] = fma(t.wj[v], other[v], red[1]);
+            red[2] = fma(t.wj[v], t.Fcar[v], red[2]);
+            red[3] = fma(t.wj[v], F1d[v], red[3]);
+            t.Fcar[v] = F2u[v];
+        } else {                         // carried = F_2_down, B_2; other = F_1_up; new B = B_1
+            two_stream_k(k[v], t.sg[v], dpg, other[v], t.Fcar[v], Bn, t.Bcar[v],
+                         F2u[v], F1d[v], dtau[v]);
+            red[0] = fma(t.wj[v], F2u[v], red[0]);
+            red[1] = fma(t.wj[v], t.Fcar[v], red[1]);
+            red[2] = fma(t.wj[v], other[v], red[2]);
+            red[3] = fma(t.wj[v], F1d[v], red[3]);
+            t.Fcar[v] = F1d[v];
+        }
+        t.Bcar[v] = Bn;
+    }
+}
+
 // One CTA = kThreads * V consecutive wavelengths of one atmosphere, all layers.  Each thread
 // carries the running stream (F_up for emit, F_down for absorb) and the Planck term of the
-// shared level in registers; the other stream is read stale from HBM and both are written
-// back.  The level records are staged into shared memory by one TMA bulk copy.
-template <typename TabT, int S_T, int DIR, int V>
-__global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
+// shared level in registers; the other stream is read stale from HBM one layer ahead of its use
+// and both are written back.  The level records are staged into shared memory by one TMA bulk
+// copy.  The loop body is a single basic block (no data-dependent or uniform branches).
+template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
+__global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
     double* sm_rec = smem;                       // [L][rec8]
-    double* sm_part = smem + (size_t)L * rec8;   // [L][kWarps][4]
+    const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
+    // this warp's wavelength-integral partials: partials[b][cta * kWarps + warp][L][4]
+    double* part = a.partials + (((int64_t)b * gridDim.x + blockIdx.x) * kWarps + warp) * L * 4;
+    const uint32_t stage = smem_u32(slot);       // [4 S][kThreads][V] staged table elements
     const int64_t n_lam = a.n_lam;
 
     // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
@@ -532,16 +602,16 @@ __global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
     const int64_t rowT = (int64_t)a.N_T * n_lam;
     double* Fu = static_cast<double*>(a.F_up) + (int64_t)b * L * n_lam + j;
     double* Fd = static_cast<double*>(a.F_down) + (int64_t)b * L * n_lam + j;
-    double* dt_out = a.dtaus ? static_cast<double*>(a.dtaus) + (int64_t)b * L * n_lam + j : nullptr;
-    double c1[V], c2[V], sg[V], wj[V];
-    Vec<V>::ldg(a.c1 + j, c1);
-    Vec<V>::ldg(a.c2 + j, c2);
-    Vec<V>::ldg(a.sigma + j, sg);
-    Vec<V>::ldg(a.w + j, wj);
+    double* dt_out = DTAUS ? static_cast<double*>(a.dtaus) + (int64_t)b * L * n_lam + j : nullptr;
+    Lane<V> t;
+    Vec<V>::ldg(a.c1 + j, t.c1);
+    Vec<V>::ldg(a.c2 + j, t.c2);
+    Vec<V>::ldg(a.sigma + j, t.sg);
+    Vec<V>::ldg(a.w + j, t.wj);
     const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
 #pragma unroll
-    for (int v = 0; v < V; ++v) { sg[v] *= sscale; if (!live) wj[v] = 0.0; }
-    if (dt_out && live) {                        // leading row of ones, twostream.py:352/:487
+    for (int v = 0; v < V; ++v) { t.sg[v] *= sscale; if (!live) t.wj[v] = 0.0; }
+    if (DTAUS && live) {                         // leading row of ones, twostream.py:352/:487
         double one[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) one[v] = 1.0;
@@ -559,107 +629,93 @@ __global__ void __launch_bounds__(kThreads) sweep_kernel(SweepArgs a) {
         }
     }
 
-    double Fcar[V], Bcar[V];                     // carried stream and carried Planck term
+    double F2u[V], F1d[V], dtau[V], red[4], oth[V], nxt[V], k[V];
     if (DIR == FREI_EMIT) {
-        double ftoa[V];
-        Vec<V>::ldg(a.f_toa + j, ftoa);
-        const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
-        Vec<V>::ld(Fu + n_lam, Fcar);                            // fluxes_up[1], stale
-        const double invT1 = sm_rec[rec8 + 1];
+        // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
+        const double* rec = sm_rec + rec8;
+        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);
+        Vec<V>::ld(Fu + n_lam, t.Fcar);                                  // fluxes_up[1], stale
+        const double invT1 = rec[1];
 #pragma unroll
-        for (int v = 0; v < V; ++v) { ftoa[v] *= fscale; Bcar[v] = planck(c1[v], c2[v], invT1); }
-        const double* pFd = Fd + 2 * n_lam;                      // fluxes_down[i + 1]
-        double* pFu_out = Fu + 2 * n_lam;                        // fluxes_up[i + 1]
-        double* pFd_out = Fd + n_lam;                            // fluxes_down[i]
-        double* pdt = dt_out ? dt_out + n_lam : nullptr;
-        for (int i = 1; i < L; ++i) {
-            const bool top = (i == L - 1);
-            const double* rec = sm_rec + (size_t)i * rec8;
-            double F2d[V], k[V];
-            if (top) {
+        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invT1);
+        const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
+        double* pFu_out = Fu + 2 * n_lam;                                // fluxes_up[i + 1]
+        double* pFd_out = Fd + n_lam;                                    // fluxes_down[i]
+        double* pdt = DTAUS ? dt_out + n_lam : nullptr;
+        if (L > 2) Vec<V>::ld(pFd, nxt);
+        cp_async_wait_all();
+        gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
+        for (int i = 1; i < L - 1; ++i) {
+            stage_rows<TabT, S_T, V>(tabj, rec + rec8, S, n_lam, rowT, stage);   // level i + 1
 #pragma unroll
-                for (int v = 0; v < V; ++v) F2d[v] = ftoa[v];    // :379-382
-            } else {
-                Vec<V>::ld(pFd, F2d);
-            }
-            gather_k<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, k);
-            const double dpg = rec[0];
-            const double invT2 = top ? 0.0 : rec[rec8 + 1];
-            double F2u[V], F1d[V], dtau[V], red[4] = {0.0, 0.0, 0.0, 0.0};
-#pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const double B2 = top ? Bcar[v] : planck(c1[v], c2[v], invT2);   // :358-363
-                two_stream_k(k[v] + sg[v], sg[v], dpg, Fcar[v], F2d[v], Bcar[v], B2,
-                             F2u[v], F1d[v], dtau[v]);
-                red[0] = fma(wj[v], F2u[v], red[0]);
-                red[1] = fma(wj[v], F2d[v], red[1]);
-                red[2] = fma(wj[v], Fcar[v], red[2]);
-                red[3] = fma(wj[v], F1d[v], red[3]);
-                Fcar[v] = F2u[v];
-                Bcar[v] = B2;
-            }
+            for (int v = 0; v < V; ++v) oth[v] = nxt[v];
+            pFd += n_lam;
+            if (i + 1 < L - 1) Vec<V>::ld(pFd, nxt);                     // one layer ahead
+            layer_step<FREI_EMIT, V, false>(t, k, rec[0], oth, rec[rec8 + 1], F2u, F1d, dtau, red);
             if (live) {
-                if (!top) Vec<V>::st(pFu_out, F2u);                           // :392-394
+                Vec<V>::st(pFu_out, F2u);                                // :392-394
                 Vec<V>::st(pFd_out, F1d);
-                if (pdt) Vec<V>::st(pdt, dtau);
+                if (DTAUS) Vec<V>::st(pdt, dtau);
             }
             const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
-            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = r4;
-            pFd += n_lam; pFu_out += n_lam; pFd_out += n_lam;
-            if (pdt) pdt += n_lam;
+            if ((lane & 7) == 0) part[i * 4 + (lane >> 3)] = r4;
+            pFu_out += n_lam; pFd_out += n_lam; rec += rec8;
+            if (DTAUS) pdt += n_lam;
+            cp_async_wait_all();
+            gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
+        }
+        {   // top: p_2 extrapolated (in the record), T_2 = T_1, F_2_down = F_TOA, F_2_up discarded
+            Vec<V>::ldg(a.f_toa + j, oth);                               // :379-382
+            const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
+#pragma unroll
+            for (int v = 0; v < V; ++v) oth[v] *= fscale;
+            layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, F2u, F1d, dtau, red);
+            if (live) {
+                Vec<V>::st(pFd_out, F1d);
+                if (DTAUS) Vec<V>::st(pdt, dtau);
+            }
+            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
+            if ((lane & 7) == 0) part[(L - 1) * 4 + (lane >> 3)] = r4;
         }
     } else {
-        Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, Fcar);                      // fluxes_down[L-1]
-        const double invTt = sm_rec[(size_t)(L - 1) * rec8 + 1];
+        const double* rec = sm_rec + (size_t)(L - 2) * rec8;
+        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);
+        Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, t.Fcar);               // fluxes_down[L-1]
+        const double invTt = rec[rec8 + 1];
 #pragma unroll
-        for (int v = 0; v < V; ++v) Bcar[v] = planck(c1[v], c2[v], invTt);
-        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;                    // fluxes_up[i], stale
-        double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                      // fluxes_up[i + 1]
-        double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                      // fluxes_down[i]
-        double* pdt = dt_out ? dt_out + n_lam : nullptr;                      // visiting order
+        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invTt);
+        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
+        double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                 // fluxes_up[i + 1]
+        double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                 // fluxes_down[i]
+        double* pdt = DTAUS ? dt_out + n_lam : nullptr;                  // visiting order
+        Vec<V>::ld(pFu, nxt);
+        cp_async_wait_all();
+        gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = L - 2; i >= 0; --i) {
-            const double* rec = sm_rec + (size_t)i * rec8;
-            double F1u[V], k[V];
-            Vec<V>::ld(pFu, F1u);                                             // :512
-            gather_k<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, k);
-            const double dpg = rec[0], invT1 = rec[1];
-            double F2u[V], F1d[V], dtau[V], red[4] = {0.0, 0.0, 0.0, 0.0};
+            if (i > 0) stage_rows<TabT, S_T, V>(tabj, rec - rec8, S, n_lam, rowT, stage);   // level i - 1
 #pragma unroll
-            for (int v = 0; v < V; ++v) {
-                const double B1 = planck(c1[v], c2[v], invT1);
-                two_stream_k(k[v] + sg[v], sg[v], dpg, F1u[v], Fcar[v], B1, Bcar[v],
-                             F2u[v], F1d[v], dtau[v]);
-                red[0] = fma(wj[v], F2u[v], red[0]);
-                red[1] = fma(wj[v], Fcar[v], red[1]);
-                red[2] = fma(wj[v], F1u[v], red[2]);
-                red[3] = fma(wj[v], F1d[v], red[3]);
-                Fcar[v] = F1d[v];
-                Bcar[v] = B1;
-            }
+            for (int v = 0; v < V; ++v) oth[v] = nxt[v];
+            pFu -= n_lam;
+            if (i > 0) Vec<V>::ld(pFu, nxt);                             // one layer ahead, :512
+            layer_step<FREI_ABSORB, V, false>(t, k, rec[0], oth, rec[1], F2u, F1d, dtau, red);
             if (live) {
-                Vec<V>::st(pFu_out, F2u);                                     // :521-522
+                Vec<V>::st(pFu_out, F2u);                                // :521-522
                 Vec<V>::st(pFd_out, F1d);
-                if (pdt) Vec<V>::st(pdt, dtau);
+                if (DTAUS) Vec<V>::st(pdt, dtau);
             }
             const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
-            if ((lane & 7) == 0) sm_part[(i * kWarps + warp) * 4 + (lane >> 3)] = r4;
-            pFu -= n_lam; pFu_out -= n_lam; pFd_out -= n_lam;
-            if (pdt) pdt += n_lam;
+            if ((lane & 7) == 0) part[i * 4 + (lane >> 3)] = r4;
+            pFu_out -= n_lam; pFd_out -= n_lam;
+            if (DTAUS) pdt += n_lam;
+            if (i > 0) {
+                rec -= rec8;
+                cp_async_wait_all();
+                gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
+            }
         }
     }
-    __syncthreads();
-    // combine the warps of this CTA in fixed order and publish [L][4]
-    double* out = a.partials + ((int64_t)b * gridDim.x + blockIdx.x) * L * 4;
-    const int i_lo = (DIR == FREI_EMIT) ? 1 : 0, i_hi = (DIR == FREI_EMIT) ? L : L - 1;
-    for (int e = tid; e < L * 4; e += kThreads) {
-        const int i = e >> 2, cidx = e & 3;
-        double s = 0.0;
-        if (i >= i_lo && i < i_hi) {
-#pragma unroll
-            for (int wq = 0; wq < kWarps; ++wq) s += sm_part[(i * kWarps + wq) * 4 + cidx];
-        }
-        out[e] = s;
-    }
+    // rows the sweep does not visit (emit: level 0, absorb: level L-1) contribute nothing
+    if (lane < 4) part[((DIR == FREI_EMIT) ? 0 : (L - 1)) * 4 + lane] = 0.0;
 }
 
 // ---------------------------------------------------------------------------
@@ -746,23 +802,32 @@ static inline int64_t sweep_blocks(int64_t n_lam) {
     return (n_lam + per - 1) / per;
 }
 
-template <typename TabT, int S_T, int DIR, int V>
+template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
 static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V>,
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V, DTAUS>,
                                   cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    sweep_kernel<TabT, S_T, DIR, V><<<grid, kThreads, smem, st>>>(a);
+    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V, DTAUS>,
+                                  cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  (int)cudaSharedmemCarveoutMaxShared));
+    sweep_kernel<TabT, S_T, DIR, V, DTAUS><<<grid, kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
+}
+
+template <typename TabT, int S_T, int DIR>
+static int launch_sweep_v(const SweepArgs& a, int V, dim3 grid, size_t smem, cudaStream_t st) {
+    if (a.dtaus)
+        return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, grid, smem, st)
+                      : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, grid, smem, st);
+    return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, false>(a, grid, smem, st)
+                  : launch_sweep_one<TabT, S_T, DIR, 1, false>(a, grid, smem, st);
 }
 
 template <typename TabT, int S_T>
 static int launch_sweep_dir(const SweepArgs& a, int direction, int V, dim3 grid, size_t smem,
                             cudaStream_t st) {
-    if (direction == FREI_EMIT)
-        return V == 2 ? launch_sweep_one<TabT, S_T, FREI_EMIT, 2>(a, grid, smem, st)
-                      : launch_sweep_one<TabT, S_T, FREI_EMIT, 1>(a, grid, smem, st);
-    return V == 2 ? launch_sweep_one<TabT, S_T, FREI_ABSORB, 2>(a, grid, smem, st)
-                  : launch_sweep_one<TabT, S_T, FREI_ABSORB, 1>(a, grid, smem, st);
+    if (direction == FREI_EMIT) return launch_sweep_v<TabT, S_T, FREI_EMIT>(a, V, grid, smem, st);
+    return launch_sweep_v<TabT, S_T, FREI_ABSORB>(a, V, grid, smem, st);
 }
 
 template <typename TabT>
@@ -791,7 +856,7 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
                               int64_t* layer_params, int64_t* partials, int64_t* sums, int64_t* dT) {
     ARG_TRY(B > 0 && L >= 3 && S > 0 && S <= kMaxS && n_lam > 0);
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
-    if (partials) *partials = (int64_t)B * sweep_blocks_max(n_lam) * L * 4 * 8;
+    if (partials) *partials = (int64_t)B * sweep_rows_max(n_lam) * L * 4 * 8;
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -899,7 +964,8 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
     const int V = sweep_V(tab->n_lam);
     dim3 grid((unsigned)sweep_blocks(tab->n_lam), atm->B);
-    const size_t smem = ((size_t)atm->L * a.lp.rec8 + (size_t)atm->L * kWarps * 4) * sizeof(double);
+    const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) +
+                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
     if (smem > 200 * 1024)
         return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
     if (tab->dtype == FREI_F32) return launch_sweep<float>(a, direction, V, grid, smem, (cudaStream_t)stream);
@@ -910,7 +976,7 @@ int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws, int64
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
     const int nw = atm->B * atm->L * 4;
     reduce_kernel<<<(nw * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        ws->partials, ws->sums, atm->B, atm->L, (int)sweep_blocks(n_lam));
+        ws->partials, ws->sums, atm->B, atm->L, (int)sweep_blocks(n_lam) * kWarps);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
