@@ -69,11 +69,13 @@ SIGNATURES = {
     'frei_b200_sweep': (C.c_int, [P(frei_table), P(frei_spectral), P(frei_atmosphere),
                                   P(frei_flux), c_int32, P(frei_workspace), c_void_p]),
     'frei_b200_reduce': (C.c_int, [P(frei_atmosphere), P(frei_workspace), c_int64, c_void_p]),
-    'frei_b200_update_T': (C.c_int, [P(frei_atmosphere), P(frei_workspace), c_int32, c_double,
-                                     c_void_p, c_void_p]),
+    'frei_b200_update_T': (C.c_int, [P(frei_table), P(frei_atmosphere), P(frei_workspace), c_int32,
+                                     c_double, c_void_p, c_void_p]),
+    'frei_b200_post': (C.c_int, [P(frei_table), P(frei_atmosphere), P(frei_workspace), c_int64,
+                                 c_int32, c_double, c_void_p, c_int32, c_void_p]),
     'frei_b200_sweep_step': (C.c_int, [P(frei_table), P(frei_spectral), P(frei_atmosphere),
                                        P(frei_flux), c_int32, c_double, P(frei_workspace),
-                                       c_void_p, c_void_p]),
+                                       c_void_p, c_int32, c_int32, c_void_p]),
 }
 
 _lib = None

@@ -282,23 +282,10 @@ class Grid(object):
 
 
 def _gather_lambda(spec_local, dtaus_local, eng, group):
-    """All-gather wavelength slices (uneven sizes) of the final spectrum and dtaus."""
-    import torch
-    import torch.distributed as dist
-    world = dist.get_world_size(group)
-    n = eng.n_lam_global
-    sizes = [shard_range(n, r, world) for r in range(world)]
-    nmax = max(hi - lo for lo, hi in sizes)
-    L = eng.L
-    buf = torch.zeros((L + 1, nmax), dtype=torch.float64, device=eng.device)
-    buf[0, :eng.n_lam] = spec_local
-    buf[1:, :eng.n_lam] = dtaus_local
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
-    spec = np.concatenate([o[0, :hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)])
-    dtaus = np.concatenate([o[1:, :hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)],
-                           axis=1)
-    return spec, dtaus
+    """All-gather the wavelength slices of the final spectrum and dtaus."""
+    from .sharding import gather_lambda
+    return (gather_lambda(spec_local, eng.n_lam_global, group),
+            gather_lambda(dtaus_local, eng.n_lam_global, group))
 
 
 # -- T_eff diagnostics (frei/core.py:386-439): cheap host post-processing ----------

@@ -58,6 +58,7 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
 constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxS = 32;
+constexpr int kPostChunks = 64;         // stage-1 CTAs of the partials reduction
 
 // ---------------------------------------------------------------------------
 // workspace layout
@@ -85,6 +86,7 @@ static inline LayerParams layer_params_view(void* p, int S) {
     v.S = S;
     return v;
 }
+static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
 static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + kWarps; }   // warps at V = 1
 
 // ---------------------------------------------------------------------------
@@ -719,22 +721,6 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
 }
 
 // ---------------------------------------------------------------------------
-// fixed-order reduction of block partials: one warp per (b, layer, component)
-// ---------------------------------------------------------------------------
-__global__ void reduce_kernel(const double* __restrict__ partials, double* __restrict__ sums,
-                              int B, int L, int nblk) {
-    const int gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-    if (gw >= B * L * 4) return;
-    const int b = gw / (L * 4), e = gw % (L * 4);
-    const double* p = partials + (int64_t)b * nblk * L * 4 + e;
-    double s = 0.0;
-    for (int k = lane; k < nblk; k += 32) s += p[(int64_t)k * L * 4];
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) sums[gw] = s;
-}
-
-// ---------------------------------------------------------------------------
 // K4: per-layer thermodynamics and the temperature update
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ double cp_of(double m_bar) { return (2.0 + 5.0) / (2.0 * m_bar) * FREI_KB; }   // :220-224
@@ -742,55 +728,115 @@ __device__ __forceinline__ double dz_of(double T, double p1, double p2, double g
     return (FREI_KB * T) / (m_bar * g) * log(p1 / p2);                                                    // :186-187
 }
 
-// One CTA per atmosphere, thread i = layer i: every read of T precedes the barrier, every
-// write follows it.
-__global__ void update_T_kernel(double* __restrict__ T, const double* __restrict__ P,
-                                const double* __restrict__ g_arr, const double* __restrict__ mbar_arr,
-                                const double* __restrict__ alpha_arr, const double* __restrict__ sums,
-                                double* __restrict__ dT_out, double* __restrict__ T_hist,
-                                int L, int direction, double alpha_override) {
-    const int b = blockIdx.x, i = threadIdx.x;
-    double* Tb = T + (int64_t)b * L;
-    const double* Pb = P + (int64_t)b * L;
+struct UpdateArgs {
+    double* T; const double* P; const double* g; const double* m_bar; const double* alpha;
+    double* dT; double* T_hist;
+    int L, direction;
+    double alpha_override;
+};
+
+// dT of level i of atmosphere b from its four wavelength integrals s[0..3]
+// (div_bol_net_flux, convective_flux, delta_t_i, delta_temperature; twostream.py:23-43, 190-287)
+__device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int i, const double* s) {
+    const int L = u.L;
+    const bool active = (u.direction == FREI_EMIT) ? (i >= 1) : (i <= L - 2);
+    if (!active) return 0.0;                                  // dT[0] = 0 (emit), dT[L-1] = 0 (absorb)
+    const double* Tb = u.T + (int64_t)b * L;
+    const double* Pb = u.P + (int64_t)b * L;
+    const double T1 = Tb[i];
+    const double g = u.g[b], m_bar = u.m_bar[b];
+    const double alpha = (u.alpha_override >= 0.0) ? u.alpha_override : u.alpha[b];
+    const double p1 = Pb[i] * FREI_BAR;
+    double p2, T2;
+    if (i == L - 1) { p2 = p1 * (Pb[L - 2] * FREI_BAR) / (Pb[L - 3] * FREI_BAR); T2 = T1; }   // :358-363
+    else { p2 = Pb[i + 1] * FREI_BAR; T2 = Tb[i + 1]; }
+    const double dF_rad = (s[0] - s[1]) - (s[2] - s[3]);                      // :199
+    const double cp = cp_of(m_bar);
+    const double dz = dz_of(T1, p1, p2, g, m_bar);
+    const double rho = ((p1 - p2) / g) / dz;                                  // :238
+    const double dgam = (T1 - T2) / dz - g / cp;                              // :241-266
+    const double lmix = alpha * FREI_KB * T1 / (m_bar * g);                   // :270
+    double F_conv = 0.0;
+    if (dgam > 0.0) F_conv = rho * cp * (lmix * lmix) * sqrt(g / T1) * pow(dgam, 1.5);   // :285-287
+    const double div = (dF_rad + F_conv) / dz;                                // :205
+    const double X = div * dz;
+    const double f_pre = (X != 0.0) ? 1e5 / pow(fabs(X), 0.9) : 1.0;          // :32-35
+    const double dt_rad = cp * p1 / FREI_SIGSB / g / (T1 * T1 * T1);          // :37
+    double dt = f_pre * dt_rad;
+    if (dgam > 0.0) dt = f_pre * fmin(dt_rad, sqrt(T1 / g / dgam));           // :39-43
+    // delta_temperature is called without m_bar: defaults 2.4 m_p, n_dof 5 (:403-405)
+    const double m_def = 2.4 * FREI_MP;
+    const double rho_def = ((p1 - p2) / g) / dz_of(T1, p1, p2, g, m_def);
+    return 1.0 / rho_def / cp_of(m_def) * div * dt;                           // :216-217
+}
+
+// Block-wide: thread i = level i.  All reads of T precede the barrier, all writes follow it;
+// then (optionally) the records of the new T are rebuilt for the next sweep.
+__device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepArgs& pa, int do_prep,
+                                                int b, const double* sums_b) {
+    const int i = threadIdx.x, L = u.L;
     double dT = 0.0, T1 = 0.0;
     if (i < L) {
-        T1 = Tb[i];
-        const bool active = (direction == FREI_EMIT) ? (i >= 1) : (i <= L - 2);
-        if (active) {
-            const double g = g_arr[b], m_bar = mbar_arr[b];
-            const double alpha = (alpha_override >= 0.0) ? alpha_override : alpha_arr[b];
-            const double p1 = Pb[i] * FREI_BAR;
-            double p2, T2;
-            if (i == L - 1) { p2 = p1 * (Pb[L - 2] * FREI_BAR) / (Pb[L - 3] * FREI_BAR); T2 = T1; }   // :358-363
-            else { p2 = Pb[i + 1] * FREI_BAR; T2 = Tb[i + 1]; }
-            const double* s = sums + ((int64_t)b * L + i) * 4;
-            const double dF_rad = (s[0] - s[1]) - (s[2] - s[3]);                      // :199
-            const double cp = cp_of(m_bar);
-            const double dz = dz_of(T1, p1, p2, g, m_bar);
-            const double rho = ((p1 - p2) / g) / dz;                                  // :238
-            const double dgam = (T1 - T2) / dz - g / cp;                              // :241-266
-            const double lmix = alpha * FREI_KB * T1 / (m_bar * g);                   // :270
-            double F_conv = 0.0;
-            if (dgam > 0.0) F_conv = rho * cp * (lmix * lmix) * sqrt(g / T1) * pow(dgam, 1.5);   // :285-287
-            const double div = (dF_rad + F_conv) / dz;                                // :205
-            const double X = div * dz;
-            const double f_pre = (X != 0.0) ? 1e5 / pow(fabs(X), 0.9) : 1.0;          // :32-35
-            const double dt_rad = cp * p1 / FREI_SIGSB / g / (T1 * T1 * T1);          // :37
-            double dt = f_pre * dt_rad;
-            if (dgam > 0.0) dt = f_pre * fmin(dt_rad, sqrt(T1 / g / dgam));           // :39-43
-            // delta_temperature is called without m_bar: defaults 2.4 m_p, n_dof 5 (:403-405)
-            const double m_def = 2.4 * FREI_MP;
-            const double rho_def = ((p1 - p2) / g) / dz_of(T1, p1, p2, g, m_def);
-            dT = 1.0 / rho_def / cp_of(m_def) * div * dt;                             // :216-217
-        }
+        T1 = u.T[(int64_t)b * L + i];
+        dT = delta_T_level(u, b, i, sums_b + i * 4);
     }
     __syncthreads();
     if (i < L) {
-        const double Tn = T1 - dT;                                                    // :407, :536
-        dT_out[(int64_t)b * L + i] = dT;
-        Tb[i] = Tn;
-        if (T_hist) T_hist[(int64_t)b * L + i] = Tn;
+        const double Tn = T1 - dT;                                            // :407, :536
+        u.dT[(int64_t)b * L + i] = dT;
+        u.T[(int64_t)b * L + i] = Tn;
+        if (u.T_hist) u.T_hist[(int64_t)b * L + i] = Tn;
     }
+    if (!do_prep) return;
+    __syncthreads();
+    if (i < L) prep_one(pa, b, i);
+}
+
+__global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums) {
+    update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4);
+}
+
+// ---------------------------------------------------------------------------
+// fixed-order reduction of the per-warp partials (+ optional fused T update and re-bracketing)
+// ---------------------------------------------------------------------------
+// grid (nchunks, B).  Stage 1: every CTA sums its chunk of partial rows.  The CTA that finishes
+// last for an atmosphere (atomic ticket) sums the chunk results in fixed chunk order — the
+// result does not depend on which CTA that is — and, on a single device, goes on to update T
+// and rebuild the level records, so one launch follows each sweep.
+struct PostArgs {
+    const double* partials; double* chunk_sums; unsigned int* counters; double* sums;
+    int rows, rows_per_chunk, nchunks;
+    int do_update, do_prep;
+};
+
+__global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
+    extern __shared__ double sm_sums[];          // [L][4]
+    __shared__ int is_last;
+    const int b = blockIdx.y, chunk = blockIdx.x, n = u.L * 4;
+    const int r0 = chunk * q.rows_per_chunk, r1 = min(q.rows, r0 + q.rows_per_chunk);
+    const double* p = q.partials + (int64_t)b * q.rows * n;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double s = 0.0;
+        for (int r = r0; r < r1; ++r) s += p[(int64_t)r * n + e];
+        q.chunk_sums[((int64_t)b * q.nchunks + chunk) * n + e] = s;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(q.counters + b, 1u) == (unsigned)(q.nchunks - 1));
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const double* cs = q.chunk_sums + (int64_t)b * q.nchunks * n;
+    for (int e = threadIdx.x; e < n; e += blockDim.x) {
+        double s = 0.0;
+        for (int c = 0; c < q.nchunks; ++c) s += cs[(int64_t)c * n + e];
+        q.sums[(int64_t)b * n + e] = s;
+        sm_sums[e] = s;
+    }
+    if (threadIdx.x == 0) q.counters[b] = 0u;    // self-cleaning for the next launch
+    if (!q.do_update) return;
+    __syncthreads();
+    update_and_prep(u, pa, q.do_prep, b, sm_sums);
 }
 
 // ---------------------------------------------------------------------------
@@ -856,7 +902,8 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
                               int64_t* layer_params, int64_t* partials, int64_t* sums, int64_t* dT) {
     ARG_TRY(B > 0 && L >= 3 && S > 0 && S <= kMaxS && n_lam > 0);
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
-    if (partials) *partials = (int64_t)B * sweep_rows_max(n_lam) * L * 4 * 8;
+    if (partials)       // per-warp rows + chunk sums + per-atmosphere tickets
+        *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4);
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -972,38 +1019,103 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     return launch_sweep<double>(a, direction, V, grid, smem, (cudaStream_t)stream);
 }
 
-int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws, int64_t n_lam, void* stream) {
+static void fill_prep(PrepArgs& a, const frei_table* tab, const frei_atmosphere* atm,
+                      const frei_workspace* ws) {
+    a.axis_P = tab->axis_P; a.axis_T = tab->axis_T; a.has_T = tab->has_T;
+    a.T = atm->T; a.P = atm->P; a.mmr = atm->mmr; a.g = atm->g;
+    a.lp = layer_params_view(ws->layer_params, tab->S);
+    a.iP = nullptr; a.iT = nullptr; a.wP = nullptr; a.wT = nullptr; a.oob = nullptr;
+    a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_P = tab->N_P; a.N_T = tab->N_T;
+    a.n_lam = tab->n_lam;
+}
+
+static void fill_update(UpdateArgs& u, const frei_atmosphere* atm, const frei_workspace* ws,
+                        int direction, double alpha_override, double* d_T_hist) {
+    u.T = atm->T; u.P = atm->P; u.g = atm->g; u.m_bar = atm->m_bar; u.alpha = atm->alpha;
+    u.dT = ws->dT; u.T_hist = d_T_hist;
+    u.L = atm->L; u.direction = direction; u.alpha_override = alpha_override;
+}
+
+// reduce (+ update T (+ rebuild records)) in one launch
+static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                       int64_t n_lam, int do_update, int do_prep, int direction,
+                       double alpha_override, double* d_T_hist, cudaStream_t st) {
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
-    const int nw = atm->B * atm->L * 4;
-    reduce_kernel<<<(nw * 32 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(
-        ws->partials, ws->sums, atm->B, atm->L, (int)sweep_blocks(n_lam) * kWarps);
+    ARG_TRY(atm->L >= 3 && atm->L <= 1024 && atm->B <= 65535);
+    PostArgs q;
+    q.rows = (int)sweep_blocks(n_lam) * kWarps;
+    q.nchunks = q.rows < kPostChunks ? q.rows : kPostChunks;
+    q.rows_per_chunk = (q.rows + q.nchunks - 1) / q.nchunks;
+    q.nchunks = (q.rows + q.rows_per_chunk - 1) / q.rows_per_chunk;
+    const int64_t n = (int64_t)atm->L * 4;
+    q.partials = ws->partials;
+    q.chunk_sums = ws->partials + (int64_t)atm->B * sweep_rows_max(n_lam) * n;
+    q.counters = reinterpret_cast<unsigned int*>(q.chunk_sums + (int64_t)atm->B * kPostChunks * n);
+    q.sums = ws->sums;
+    q.do_update = do_update; q.do_prep = do_prep;
+    UpdateArgs u{};
+    PrepArgs pa{};
+    if (do_update) {
+        ARG_TRY(ws->dT && atm->T && atm->P && atm->g && atm->m_bar && atm->alpha);
+        ARG_TRY(direction == FREI_EMIT || direction == FREI_ABSORB);
+        fill_update(u, atm, ws, direction, alpha_override, d_T_hist);
+    } else {
+        u.L = atm->L;
+    }
+    if (do_prep) {
+        int rc = check_common(tab, atm, ws);
+        if (rc) return rc;
+        fill_prep(pa, tab, atm, ws);
+    }
+    int threads = ((atm->L + 31) / 32) * 32;
+    if (threads < 256) threads = 256;
+    post_kernel<<<dim3(q.nchunks, atm->B), threads, (size_t)n * sizeof(double), st>>>(q, u, pa);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
 
-int frei_b200_update_T(const frei_atmosphere* atm, const frei_workspace* ws, int32_t direction,
-                       double alpha_override, double* d_T_hist, void* stream) {
+int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws, int64_t n_lam, void* stream) {
+    return launch_post(nullptr, atm, ws, n_lam, 0, 0, FREI_EMIT, -1.0, nullptr, (cudaStream_t)stream);
+}
+
+int frei_b200_update_T(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                       int32_t direction, double alpha_override, double* d_T_hist, void* stream) {
     ARG_TRY(atm && ws && ws->sums && ws->dT && atm->T && atm->P && atm->g && atm->m_bar && atm->alpha);
     ARG_TRY(atm->L >= 3 && atm->L <= 1024);
     ARG_TRY(direction == FREI_EMIT || direction == FREI_ABSORB);
+    UpdateArgs u{};
+    PrepArgs pa{};
+    fill_update(u, atm, ws, direction, alpha_override, d_T_hist);
+    if (tab) {
+        int rc = check_common(tab, atm, ws);
+        if (rc) return rc;
+        fill_prep(pa, tab, atm, ws);
+    }
     const int threads = ((atm->L + 31) / 32) * 32;
-    update_T_kernel<<<atm->B, threads, 0, (cudaStream_t)stream>>>(
-        atm->T, atm->P, atm->g, atm->m_bar, atm->alpha, ws->sums, ws->dT, d_T_hist,
-        atm->L, direction, alpha_override);
+    update_prep_kernel<<<atm->B, threads, 0, (cudaStream_t)stream>>>(u, pa, tab ? 1 : 0, ws->sums);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
+}
+
+int frei_b200_post(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                   int64_t n_lam, int32_t direction, double alpha_override, double* d_T_hist,
+                   int32_t prep_next, void* stream) {
+    return launch_post(tab, atm, ws, n_lam, 1, prep_next ? 1 : 0, direction, alpha_override, d_T_hist,
+                       (cudaStream_t)stream);
 }
 
 int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec, const frei_atmosphere* atm,
                          const frei_flux* flux, int32_t direction, double alpha_override,
-                         const frei_workspace* ws, double* d_T_hist, void* stream) {
-    int rc = frei_b200_layer_prep(tab, atm, ws, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
-    if (rc) return rc;
+                         const frei_workspace* ws, double* d_T_hist, int32_t prep_first,
+                         int32_t prep_next, void* stream) {
+    int rc;
+    if (prep_first) {
+        rc = frei_b200_layer_prep(tab, atm, ws, nullptr, nullptr, nullptr, nullptr, nullptr, stream);
+        if (rc) return rc;
+    }
     rc = frei_b200_sweep(tab, spec, atm, flux, direction, ws, stream);
     if (rc) return rc;
-    rc = frei_b200_reduce(atm, ws, tab->n_lam, stream);
-    if (rc) return rc;
-    return frei_b200_update_T(atm, ws, direction, alpha_override, d_T_hist, stream);
+    return frei_b200_post(tab, atm, ws, tab->n_lam, direction, alpha_override, d_T_hist, prep_next, stream);
 }
 
 }  // extern "C"

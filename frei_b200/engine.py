@@ -19,6 +19,7 @@ import numpy as np
 
 from . import _cabi
 from ._cabi import FREI_EMIT, FREI_ABSORB, FREI_F32, FREI_F64
+from .sharding import shard_range, allreduce_sums
 
 __all__ = ['DeviceTable', 'Engine', 'FREI_EMIT', 'FREI_ABSORB', 'shard_range']
 
@@ -26,13 +27,6 @@ __all__ = ['DeviceTable', 'Engine', 'FREI_EMIT', 'FREI_ABSORB', 'shard_range']
 def _torch():
     import torch
     return torch
-
-
-def shard_range(n, rank, world):
-    """Contiguous slice [lo, hi) of an axis of length n owned by ``rank`` of ``world``."""
-    base, rem = divmod(int(n), int(world))
-    lo = rank * base + min(rank, rem)
-    return lo, lo + base + (1 if rank < rem else 0)
 
 
 def normalise_table(tab):
@@ -205,10 +199,11 @@ class Engine:
         sizes = [C.c_int64() for _ in range(4)]
         _cabi.check(self.lib.frei_b200_workspace_bytes(B, L, S, n, *[C.byref(s) for s in sizes]))
         self._lp = torch.empty(sizes[0].value, dtype=torch.uint8, device=dev)
-        self._partials = torch.empty(sizes[1].value // 8, dtype=f64, device=dev)
+        self._partials = torch.zeros((sizes[1].value + 7) // 8, dtype=f64, device=dev)   # incl. ticket counters
         self.sums = torch.zeros((B, L, 4), dtype=f64, device=dev)
         self.dT = torch.zeros((B, L), dtype=f64, device=dev)
         self.launches = 0
+        self._records_stale = True     # level records must be rebuilt before the next sweep
         self.sweep_events = None        # list of (start, end) CUDA events around the sweep kernel
         self._build_structs()
 
@@ -236,11 +231,13 @@ class Engine:
     # -- state --------------------------------------------------------------
     def set_T(self, T):
         torch = _torch()
+        self._records_stale = True
         self.T.copy_(torch.from_numpy(np.ascontiguousarray(
             np.broadcast_to(np.asarray(T, dtype=np.float64), (self.B, self.L)))))
 
     def set_mmr(self, mmr):
         torch = _torch()
+        self._records_stale = True
         self.mmr.copy_(torch.from_numpy(np.ascontiguousarray(
             np.broadcast_to(np.asarray(mmr, dtype=np.float64), (self.B, self.L, self.S)))))
 
@@ -271,6 +268,7 @@ class Engine:
         _cabi.check(self.lib.frei_b200_layer_prep(C.byref(self._tab), C.byref(self._atm),
                                                   C.byref(self._ws), *args, self._stream()))
         self.launches += 1
+        self._records_stale = False
         return out
 
     def kappa(self):
@@ -298,15 +296,18 @@ class Engine:
         flux = self._flux_struct(with_dtaus)
         st = self._stream()
         hist_ptr = None if T_hist is None else T_hist.data_ptr()
+        prep_first = 1 if self._records_stale else 0
         if self.group is None and self.sweep_events is None:
             _cabi.check(self.lib.frei_b200_sweep_step(
                 C.byref(self._tab), C.byref(self._spec), C.byref(self._atm), C.byref(flux),
-                direction, float(alpha_override), C.byref(self._ws), hist_ptr, st))
-            self.launches += 4
+                direction, float(alpha_override), C.byref(self._ws), hist_ptr, prep_first, 1, st))
+            self.launches += 2 + prep_first
+            self._records_stale = False
             return
-        _cabi.check(self.lib.frei_b200_layer_prep(C.byref(self._tab), C.byref(self._atm),
-                                                  C.byref(self._ws), None, None, None, None,
-                                                  None, st))
+        if prep_first:
+            _cabi.check(self.lib.frei_b200_layer_prep(C.byref(self._tab), C.byref(self._atm),
+                                                      C.byref(self._ws), None, None, None, None,
+                                                      None, st))
         if self.sweep_events is not None:
             torch = _torch()
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
@@ -317,14 +318,20 @@ class Engine:
         if self.sweep_events is not None:
             ev[1].record()
             self.sweep_events.append(ev)
-        _cabi.check(self.lib.frei_b200_reduce(C.byref(self._atm), C.byref(self._ws),
-                                              self.n_lam, st))
-        if self.group is not None:
-            import torch.distributed as dist
-            dist.all_reduce(self.sums, op=dist.ReduceOp.SUM, group=self.group)
-        _cabi.check(self.lib.frei_b200_update_T(C.byref(self._atm), C.byref(self._ws), direction,
-                                                float(alpha_override), hist_ptr, st))
-        self.launches += 4
+        if self.group is None:
+            _cabi.check(self.lib.frei_b200_post(C.byref(self._tab), C.byref(self._atm),
+                                                C.byref(self._ws), self.n_lam, direction,
+                                                float(alpha_override), hist_ptr, 1, st))
+            self.launches += 2 + prep_first
+        else:
+            _cabi.check(self.lib.frei_b200_reduce(C.byref(self._atm), C.byref(self._ws),
+                                                  self.n_lam, st))
+            allreduce_sums(self.sums, self.group)
+            _cabi.check(self.lib.frei_b200_update_T(C.byref(self._tab), C.byref(self._atm),
+                                                    C.byref(self._ws), direction,
+                                                    float(alpha_override), hist_ptr, st))
+            self.launches += 3 + prep_first
+        self._records_stale = False
 
     def emit(self, **kw):
         self.sweep(FREI_EMIT, **kw)

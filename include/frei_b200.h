@@ -102,7 +102,9 @@ typedef struct {
 /* Scratch owned by the caller; sizes from frei_b200_workspace_bytes(). */
 typedef struct {
     void*   layer_params;  /* written by layer_prep, read by kappa / sweep */
-    double* partials;      /* written by sweep, read by reduce             */
+    double* partials;      /* written by sweep, read by reduce; must be zero-filled once
+                              before first use (the library leaves its ticket counters
+                              at zero after every call)                    */
     double* sums;          /* [B][L][4]: wavelength integrals of F2_up, F2_down, F1_up,
                               F1_down per layer-step (the four bolometric_flux calls,
                               frei/twostream.py:396-398, 524-527)          */
@@ -168,7 +170,7 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec,
                     const frei_atmosphere* atm, const frei_flux* flux,
                     int32_t direction, const frei_workspace* ws, void* stream);
 
-/* Deterministic fixed-order reduction of the block partials into ws->sums. */
+/* Deterministic fixed-order reduction of the per-warp partials into ws->sums. */
 int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws,
                      int64_t n_lam, void* stream);
 
@@ -177,18 +179,26 @@ int frei_b200_reduce(const frei_atmosphere* atm, const frei_workspace* ws,
  * (frei/twostream.py:23-43, 190-287) and T <- T - dT (:407, :536).
  * alpha_override >= 0 replaces atm->alpha (the final emit of
  * Grid.emission_spectrum does not forward alpha, frei/core.py:323-333).
- * d_T_hist (nullable) receives the new T as one extra [B][L] record. */
-int frei_b200_update_T(const frei_atmosphere* atm, const frei_workspace* ws,
-                       int32_t direction, double alpha_override,
+ * d_T_hist (nullable) receives the new T as one extra [B][L] record.
+ * tab (nullable): when given, the level records are rebuilt for the new T in
+ * the same launch (= layer_prep for the next sweep). */
+int frei_b200_update_T(const frei_table* tab, const frei_atmosphere* atm,
+                       const frei_workspace* ws, int32_t direction, double alpha_override,
                        double* d_T_hist, void* stream);
 
-/* Convenience for one device: layer_prep + sweep + reduce + update_T, i.e. one
- * emit()/absorb() call of the reference with n_timesteps=1
- * (frei/core.py:275-299). */
+/* Single-device fusion of reduce + update_T (+ layer_prep for the next sweep when
+ * prep_next != 0) in one launch. */
+int frei_b200_post(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                   int64_t n_lam, int32_t direction, double alpha_override, double* d_T_hist,
+                   int32_t prep_next, void* stream);
+
+/* Convenience for one device: [layer_prep if prep_first] + sweep + post, i.e. one
+ * emit()/absorb() call of the reference with n_timesteps=1 (frei/core.py:275-299). */
 int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec,
                          const frei_atmosphere* atm, const frei_flux* flux,
                          int32_t direction, double alpha_override,
-                         const frei_workspace* ws, double* d_T_hist, void* stream);
+                         const frei_workspace* ws, double* d_T_hist,
+                         int32_t prep_first, int32_t prep_next, void* stream);
 
 #ifdef __cplusplus
 }
