@@ -223,52 +223,56 @@ __device__ __forceinline__ double fast_sqrt(double x, double& rs) {
     y = fma(y, e, y);
     e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
-    double g = x * y;
-    const double d = fma(-g, g, x);
-    g = fma(d, 0.5 * y, g);
     rs = y;
-    return g;
+    return x * y;                   // ~1.5 ulp; the extra correction step is not worth 3 fp64 slots
 }
 
-// For u >= 0: T = exp(-u) and m = 1 - exp(-u), both to ~1 ulp (m without cancellation).
-// When the reduced argument needs no scaling (u < ln2/2, returned as `small`), uq = u Q(-u) =
-// 1 - m/u is also returned: it lets the caller form (T - 1)/u + 1 without cancellation.
-__device__ __forceinline__ void exp_neg(double u, double& T, double& m, double& uq, bool& small) {
-    const double MAGIC = 6755399441055744.0;             // 1.5 * 2^52
-    u = fmin(u, 1400.0);                                 // exp(-1400) == 0 in fp64
-    const double tk = fma(-u, 1.4426950408889634, MAGIC);
-    const int ki = __double2loint(tk);                   // k = rint(-u / ln 2) <= 0
-    const double k = tk - MAGIC;
-    double s = fma(k, -6.93147180369123816490e-01, -u);  // ln2 hi
-    s = fma(k, -1.90821492927058770002e-10, s);          // ln2 lo;  |s| <= 0.3466
-    // expm1(s) = s + s^2 Q(s), Q = sum_{n>=2} s^(n-2) / n! through s^13, evaluated with Estrin's
-    // scheme (dependency depth 4 instead of 12: the sweep is bound by fp64 latency chains)
-    const double s2 = s * s, s4 = s2 * s2, s8 = s4 * s4;
-    const double a0 = fma(1.6666666666666666e-01, s, 0.5);                       // 1/3!, 1/2!
-    const double a1 = fma(8.333333333333333e-03, s, 4.1666666666666664e-02);     // 1/5!, 1/4!
-    const double a2 = fma(1.984126984126984e-04, s, 1.388888888888889e-03);      // 1/7!, 1/6!
-    const double a3 = fma(2.7557319223985893e-06, s, 2.48015873015873e-05);      // 1/9!, 1/8!
-    const double a4 = fma(2.505210838544172e-08, s, 2.755731922398589e-07);      // 1/11!, 1/10!
-    const double a5 = fma(1.6059043836821613e-10, s, 2.08767569878681e-09);      // 1/13!, 1/12!
-    const double b0 = fma(a1, s2, a0), b1 = fma(a3, s2, a2), b2 = fma(a5, s2, a4);
-    const double q = fma(b2, s8, fma(b1, s4, b0));
-    const double p = fma(s2, q, s);                      // expm1(s)
-    const int ka = ki >> 1, kb = ki - ka;                // two-step scaling survives ki < -1022
-    const double sc1 = __hiloint2double((ka + 1023) << 20, 0);
-    const double sc2 = __hiloint2double((kb + 1023) << 20, 0);
-    T = (1.0 + p) * sc1 * sc2;
-    small = (ki == 0);
+// 2^(j/32), j = 0..31 (correctly rounded); copied to shared memory by the kernels that use it
+__constant__ double kExp2Tab[32] = {
+    1, 1.0218971486541166, 1.0442737824274138, 1.0671404006768237,
+    1.0905077326652577, 1.1143867425958924, 1.1387886347566916, 1.1637248587775775,
+    1.189207115002721, 1.215247359980469, 1.241857812073484, 1.2690509571917332,
+    1.2968395546510096, 1.3252366431597413, 1.3542555469368927, 1.383909881963832,
+    1.4142135623730951, 1.4451808069770467, 1.4768261459394993, 1.5091644275934228,
+    1.5422108254079407, 1.5759808451078865, 1.6104903319492543, 1.6457554781539649,
+    1.681792830507429, 1.7186192981224779, 1.7562521603732995, 1.7947090750031072,
+    1.8340080864093424, 1.8741676341103, 1.9152065613971474, 1.9571441241754002};
+
+// For u >= 0: T = exp(-u) and m = 1 - exp(-u).  -u = n ln2/32 + r with |r| <= ln2/64, so
+// exp(-u) = 2^(n >> 5) * 2^((n & 31)/32) * (1 + p(r)) with a degree-6 p: 14 fp64 instructions with
+// mostly constant operands (the fp64 pipe issues 3-register DFMAs at 2/3 rate).
+// T is good to ~1.5 ulp; m = -p when n == 0 (u <= 0.0108, no cancellation), else 1 - T.
+// uq = u Q(r) = 1 - m/u is valid when `small` (n == 0) and lets the caller form (T - 1)/u + 1
+// without cancellation.  exp(-u) is flushed to exp(-708) ~ 3e-308 beyond u = 708.
+__device__ __forceinline__ void exp_neg(double u, const double* tab, double& T, double& m, double& uq,
+                                        bool& small) {
+    const double MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
+    u = fmin(u, 708.0);
+    const double tn = fma(u, -46.166241308446828, MAGIC);      // -u * 32 / ln 2
+    const int n = __double2loint(tn);                          // rint, <= 0
+    const double fn = tn - MAGIC;
+    double r = fma(fn, -0.021660849392446835, -u);             // ln2/32 hi (36 bits: n * hi exact)
+    r = fma(fn, -5.1456092446553382e-14, r);                   // ln2/32 lo
+    double q = fma(1.3888888888888889e-03, r, 8.3333333333333332e-03);   // 1/6!, 1/5!
+    q = fma(q, r, 4.1666666666666664e-02);                     // 1/4!
+    q = fma(q, r, 1.6666666666666666e-01);                     // 1/3!
+    q = fma(q, r, 0.5);                                        // 1/2!
+    const double p = fma(r * r, q, r);                         // expm1(r)
+    const double t0 = tab[n & 31];
+    const double sc = __hiloint2double(((n >> 5) + 1023) << 20, 0);      // 2^(n >> 5), n >> 5 >= -1022
+    T = fma(t0, p, t0) * sc;
+    small = (n == 0);
     m = small ? -p : 1.0 - T;
     uq = u * q;
 }
-__device__ __forceinline__ void exp_neg(double u, double& T, double& m) {
+__device__ __forceinline__ void exp_neg(double u, const double* tab, double& T, double& m) {
     double uq; bool small;
-    exp_neg(u, T, m, uq, small);
+    exp_neg(u, tab, T, m, uq, small);
 }
 
-__device__ __forceinline__ double planck(double c1, double c2, double invT) {
+__device__ __forceinline__ double planck(double c1, double c2, double invT, const double* tab) {
     double e, m;                                         // c1 / expm1(x) = c1 e^-x / (1 - e^-x)
-    exp_neg(c2 * invT, e, m);                            // twostream.py:64-67
+    exp_neg(c2 * invT, tab, e, m);                       // twostream.py:64-67
     return c1 * e * fast_rcp(m);
 }
 
@@ -281,8 +285,8 @@ __device__ __forceinline__ double planck(double c1, double c2, double invT) {
 // ("conditioning"); this one tracks the exact value of the same formulas.
 // k = total opacity (includes sigma, opacity.py:269), sg = sigma, dpg = (p1 - p2)/g.
 __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, double F1u, double F2d,
-                                             double B1, double B2, double& F2u, double& F1d,
-                                             double& dtau) {
+                                             double B1, double B2, const double* tab, double& F2u,
+                                             double& F1d, double& dtau) {
     dtau = dpg * k;                                                     // :371-373
     const double R1 = fast_rcp(sg + k);
     const double w0 = sg * R1, omw = k * R1;                            // omega0 (:376-378), 1 - omega0
@@ -299,7 +303,7 @@ __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, do
     const double u = 2.0 * a * dtau;                                    // T = exp(-u), :139
     double Tr, m, uq;
     bool small;
-    exp_neg(u, Tr, m, uq, small);
+    exp_neg(u, tab, Tr, m, uq, small);
     const double opr = 1.0 + r;
     const double R2 = fast_rcp(opr * u);
     const double z = 0.5 * (w0 * invE) * (u * R2);                      // zeta_minus, :145
@@ -320,10 +324,11 @@ __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, do
 
 // propagate_fluxes() signature: delta_tau and omega_0 given (twostream.py:97-99).
 __device__ __forceinline__ void two_stream(double dtau, double w0, double F1u, double F2d,
-                                           double B1, double B2, double& F2u, double& F1d) {
+                                           double B1, double B2, const double* tab, double& F2u,
+                                           double& F1d) {
     // any (k, sigma, dpg) with sigma/(sigma+k) = w0 and dpg*k = dtau reproduces the inputs
     double unused;
-    two_stream_k(1.0 - w0, w0, dtau / (1.0 - w0), F1u, F2d, B1, B2, F2u, F1d, unused);
+    two_stream_k(1.0 - w0, w0, dtau / (1.0 - w0), F1u, F2d, B1, B2, tab, F2u, F1d, unused);
 }
 
 // ---------------------------------------------------------------------------
@@ -331,13 +336,16 @@ __device__ __forceinline__ void two_stream(double dtau, double w0, double F1u, d
 // ---------------------------------------------------------------------------
 __global__ void debug_math_kernel(const double* __restrict__ x, double* __restrict__ out, int64_t n) {
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n) return;
-    const double v = x[j];
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __syncthreads();
+    const double v = x[j < n ? j : n - 1];
     double rs, T, m;
+    if (j >= n) return;
     out[j] = fast_rcp(v);
     out[n + j] = fast_sqrt(v, rs);
     out[2 * n + j] = rs;
-    exp_neg(v, T, m);
+    exp_neg(v, tab, T, m);
     out[3 * n + j] = T;
     out[4 * n + j] = m;
 }
@@ -378,6 +386,9 @@ __global__ void propagate_kernel(const double* __restrict__ lam, const double* _
                                  const double* __restrict__ F2d, double T1, double T2,
                                  const double* __restrict__ dtau, const double* __restrict__ w0,
                                  double* __restrict__ F2u, double* __restrict__ F1d, int64_t n) {
+    __shared__ double tab[32];
+    if (threadIdx.x < 32) tab[threadIdx.x] = kExp2Tab[threadIdx.x];
+    __syncthreads();
     const int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n) return;
     const double l = lam[j];
@@ -385,7 +396,7 @@ __global__ void propagate_kernel(const double* __restrict__ lam, const double* _
     const double B1 = c1 / expm1(FREI_H * FREI_C / (l * FREI_KB * T1));
     const double B2 = c1 / expm1(FREI_H * FREI_C / (l * FREI_KB * T2));
     double a, d;
-    two_stream(dtau[j], w0[j], F1u[j], F2d[j], B1, B2, a, d);
+    two_stream(dtau[j], w0[j], F1u[j], F2d[j], B1, B2, tab, a, d);
     F2u[j] = a; F1d[j] = d;
 }
 
@@ -429,6 +440,24 @@ template <> struct Vec<1> {
     static __device__ __forceinline__ void ldg(const float* p, double* o) { o[0] = (double)__ldg(p); }
     static __device__ __forceinline__ void st(double* p, const double* v) { *p = v[0]; }
 };
+template <> struct Vec<4> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) {
+        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
+        const double2 s = *reinterpret_cast<const double2*>(p + 2); o[2] = s.x; o[3] = s.y;
+    }
+    static __device__ __forceinline__ void ldg(const double* p, double* o) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
+        const double2 s = __ldg(reinterpret_cast<const double2*>(p) + 1); o[2] = s.x; o[3] = s.y;
+    }
+    static __device__ __forceinline__ void ldg(const float* p, double* o) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
+        o[0] = (double)t.x; o[1] = (double)t.y; o[2] = (double)t.z; o[3] = (double)t.w;
+    }
+    static __device__ __forceinline__ void st(double* p, const double* v) {
+        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
+        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
+    }
+};
 template <> struct Vec<2> {
     static __device__ __forceinline__ void ld(const double* p, double* o) {
         const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
@@ -450,7 +479,14 @@ template <> struct Vec<2> {
 // private to it, so no CTA barrier is involved — only cp.async.wait_group.
 template <int BYTES>
 __device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst), "l"(src), "n"(BYTES) : "memory");
+    if (BYTES == 32) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
+                     ::"r"(dst + 16), "l"((const char*)src + 16) : "memory");
+    } else {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
+                     ::"r"(dst), "l"(src), "n"(BYTES == 32 ? 16 : BYTES) : "memory");
+    }
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
@@ -478,6 +514,16 @@ template <int V> struct SVec;
 template <> struct SVec<1> {
     static __device__ __forceinline__ void ld(const double* p, double* o) { o[0] = *p; }
     static __device__ __forceinline__ void ld(const float* p, double* o) { o[0] = (double)*p; }
+};
+template <> struct SVec<4> {
+    static __device__ __forceinline__ void ld(const double* p, double* o) {
+        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
+        const double2 s = *reinterpret_cast<const double2*>(p + 2); o[2] = s.x; o[3] = s.y;
+    }
+    static __device__ __forceinline__ void ld(const float* p, double* o) {
+        const float4 t = *reinterpret_cast<const float4*>(p);
+        o[0] = (double)t.x; o[1] = (double)t.y; o[2] = (double)t.z; o[3] = (double)t.w;
+    }
 };
 template <> struct SVec<2> {
     static __device__ __forceinline__ void ld(const double* p, double* o) {
@@ -535,14 +581,14 @@ struct Lane {
 // wavelength-integral contributions of this warp, and optionally delta_tau.
 template <int DIR, int V, bool SAME_T>
 __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double dpg, const double* other,
-                                           double invTn, double* F2u, double* F1d, double* dtau,
-                                           double* red) {
+                                           double invTn, const double* tab, double* F2u, double* F1d,
+                                           double* dtau, double* red) {
     red[0] = red[1] = red[2] = red[3] = 0.0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-        const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn);
+        const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn, tab);
         if (DIR == FREI_EMIT) {          // carried = F_1_up, B_1; other = F_2_down; new B = B_2
-            two_stream_k(k[v], t.sg[v], dpg, t.Fcar[v], other[v], t.Bcar[v], Bn,
+            two_stream_k(k[v], t.sg[v], dpg, t.Fcar[v], other[v], t.Bcar[v], Bn, tab,
                          F2u[v], F1d[v], dtau[v]);
             red[0] = fma(t.wj[v], F2u[v], red[0]);
             red[1] = fma(t.wj[v], other[v], red[1]);
@@ -550,7 +596,7 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
             red[3] = fma(t.wj[v], F1d[v], red[3]);
             t.Fcar[v] = F2u[v];
         } else {                         // carried = F_2_down, B_2; other = F_1_up; new B = B_1
-            two_stream_k(k[v], t.sg[v], dpg, other[v], t.Fcar[v], Bn, t.Bcar[v],
+            two_stream_k(k[v], t.sg[v], dpg, other[v], t.Fcar[v], Bn, t.Bcar[v], tab,
                          F2u[v], F1d[v], dtau[v]);
             red[0] = fma(t.wj[v], F2u[v], red[0]);
             red[1] = fma(t.wj[v], t.Fcar[v], red[1]);
@@ -571,9 +617,11 @@ template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
 __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
+    __shared__ double tab[32];                   // 2^(j/32) for exp_neg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
+    if (tid < 32) tab[tid] = kExp2Tab[tid];
     double* sm_rec = smem;                       // [L][rec8]
     const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
     // this warp's wavelength-integral partials: partials[b][cta * kWarps + warp][L][4]
@@ -639,7 +687,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
         Vec<V>::ld(Fu + n_lam, t.Fcar);                                  // fluxes_up[1], stale
         const double invT1 = rec[1];
 #pragma unroll
-        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invT1);
+        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invT1, tab);
         const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
         double* pFu_out = Fu + 2 * n_lam;                                // fluxes_up[i + 1]
         double* pFd_out = Fd + n_lam;                                    // fluxes_down[i]
@@ -653,7 +701,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFd += n_lam;
             if (i + 1 < L - 1) Vec<V>::ld(pFd, nxt);                     // one layer ahead
-            layer_step<FREI_EMIT, V, false>(t, k, rec[0], oth, rec[rec8 + 1], F2u, F1d, dtau, red);
+            layer_step<FREI_EMIT, V, false>(t, k, rec[0], oth, rec[rec8 + 1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :392-394
                 Vec<V>::st(pFd_out, F1d);
@@ -671,7 +719,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
             const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] *= fscale;
-            layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, F2u, F1d, dtau, red);
+            layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
@@ -685,7 +733,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
         Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, t.Fcar);               // fluxes_down[L-1]
         const double invTt = rec[rec8 + 1];
 #pragma unroll
-        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invTt);
+        for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invTt, tab);
         const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
         double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                 // fluxes_up[i + 1]
         double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                 // fluxes_down[i]
@@ -699,7 +747,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFu -= n_lam;
             if (i > 0) Vec<V>::ld(pFu, nxt);                             // one layer ahead, :512
-            layer_step<FREI_ABSORB, V, false>(t, k, rec[0], oth, rec[1], F2u, F1d, dtau, red);
+            layer_step<FREI_ABSORB, V, false>(t, k, rec[0], oth, rec[1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :521-522
                 Vec<V>::st(pFd_out, F1d);
@@ -842,7 +890,14 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
 // ---------------------------------------------------------------------------
 // host side of the ABI
 // ---------------------------------------------------------------------------
-static inline int sweep_V(int64_t n_lam) { return (n_lam % 2 == 0) ? 2 : 1; }
+#ifndef SWEEP_V
+#define SWEEP_V 2                 // wavelengths per thread when n_lam allows (experiment knob: 1, 2, 4)
+#endif
+static inline int sweep_V(int64_t n_lam) {
+    if (SWEEP_V == 4 && n_lam % 4 == 0) return 4;
+    if (SWEEP_V >= 2 && n_lam % 2 == 0) return 2;
+    return 1;
+}
 static inline int64_t sweep_blocks(int64_t n_lam) {
     const int64_t per = (int64_t)kThreads * sweep_V(n_lam);
     return (n_lam + per - 1) / per;
@@ -862,6 +917,11 @@ static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStre
 
 template <typename TabT, int S_T, int DIR>
 static int launch_sweep_v(const SweepArgs& a, int V, dim3 grid, size_t smem, cudaStream_t st) {
+#if SWEEP_V == 4
+    if (V == 4)
+        return a.dtaus ? launch_sweep_one<TabT, S_T, DIR, 4, true>(a, grid, smem, st)
+                       : launch_sweep_one<TabT, S_T, DIR, 4, false>(a, grid, smem, st);
+#endif
     if (a.dtaus)
         return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, grid, smem, st)
                       : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, grid, smem, st);
@@ -1011,7 +1071,10 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
     const int V = sweep_V(tab->n_lam);
     dim3 grid((unsigned)sweep_blocks(tab->n_lam), atm->B);
-    const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) +
+#ifndef SWEEP_SMEM_PAD
+#define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
+#endif
+    const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
                         (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
     if (smem > 200 * 1024)
         return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");

@@ -2,7 +2,7 @@
 torchrun --nproc-per-node N scripts/dist_parity.py
 Wavelength-sharded Grid.emission_spectrum over NCCL vs the single-GPU run of the same problem
 (every rank computes both): spectrum, T history, dtaus must agree to rounding of the summation
-order (<= 1e-12 relative on fluxes, 1e-9 K on temperatures), same iteration count.
+order (<= 1e-9 relative on fluxes, 1e-6 K on temperatures after 40 iterations), same iteration count.
 """
 import os
 import sys
@@ -38,8 +38,8 @@ def solve(group):
 (s1, T1, h1, d1), n1 = solve(None)
 (s2, T2, h2, d2), n2 = solve(dist.group.WORLD)
 rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-250)))
-ok = (n1 == n2 and rel(s2.flux, s1.flux) < 1e-11 and np.abs(T2 - T1).max() < 1e-8
-      and h1.shape == h2.shape and np.abs(h2 - h1).max() < 1e-8 and rel(d2, d1) < 1e-12)
+ok = (n1 == n2 and rel(s2.flux, s1.flux) < 1e-9 and np.abs(T2 - T1).max() < 1e-6
+      and h1.shape == h2.shape and np.abs(h2 - h1).max() < 1e-6 and rel(d2, d1) < 1e-10)
 print(f'rank {rank}: iterations {n1}/{n2} spectrum rel {rel(s2.flux, s1.flux):.2e} '
       f'T {np.abs(T2 - T1).max():.2e} K dtaus {rel(d2, d1):.2e} -> {"OK" if ok else "MISMATCH"}', flush=True)
 flag = torch.tensor([0 if ok else 1], device='cuda')
