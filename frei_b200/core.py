@@ -123,6 +123,31 @@ def converged_layers(temp_hists, dT, n_zero_crossings, convergence_dT):
     return (flips > n_zero_crossings) | (np.abs(dT) < convergence_dT), temp_hist
 
 
+class _PinnedOutputs:
+    """
+    Page-locked host buffers for the large results (spectrum, dtaus).  Allocating and pinning
+    ~n_layers x n_lambda doubles costs more than a whole solve, so a buffer is reused once the
+    arrays handed out from it have been garbage-collected by the caller.
+    """
+
+    def __init__(self):
+        self._free = {}
+        self._out = []
+
+    def get(self, shape):
+        import torch
+        self._out = [(ref, buf) for ref, buf in self._out if ref() is not None or
+                     self._free.setdefault(tuple(buf.shape), []).append(buf)]
+        pool = self._free.get(tuple(shape), [])
+        return pool.pop() if pool else torch.empty(shape, dtype=torch.float64).pin_memory()
+
+    def hand_out(self, buf):
+        import weakref
+        arr = buf.numpy()
+        self._out.append((weakref.ref(arr), buf))
+        return arr
+
+
 class Grid(object):
     """Grid over temperatures, pressures and wavelengths (frei/core.py:109-338)."""
 
@@ -150,6 +175,7 @@ class Grid(object):
         self.opacities = None
         self._table = None
         self.table_dtype = FREI_F64
+        self._outputs = _PinnedOutputs()
 
     def __repr__(self):
         T = U.value(self.init_temperatures, 'K')
@@ -224,7 +250,6 @@ class Grid(object):
         every sweep (default: only when pyfastchem is installed; the mock's
         ratios do not depend on T).
         """
-        import torch
         if self.opacities is None:
             raise ValueError("Must load opacities before computing emission spectrum.")
         conv_dT = float(U.value(convergence_dT, 'K'))
@@ -234,27 +259,24 @@ class Grid(object):
                 dynamic_chemistry = True
             except ImportError:
                 dynamic_chemistry = False
-        eng = self.make_engine(group=group)
+        eng = self._solver_engine(group)
         P = U.value(self.pressures, 'bar')
         m_bar_g = float(U.value(self.planet.m_bar, 'g'))
         L = eng.L
-        hist_dev = torch.empty((3, 1, L), dtype=torch.float64, device=eng.device)
-        hist_host = torch.empty((3, 1, L), dtype=torch.float64).pin_memory()
         temp_hists = []
         self.n_iterations = 0
         for it in range(n_timesteps):
             if dynamic_chemistry and it > 0:
                 eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
-            eng.sweep(FREI_EMIT, T_hist=hist_dev[0])
             if dynamic_chemistry:
+                eng.sweep(FREI_EMIT, T_hist=eng.hist[0])
                 eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
-            eng.sweep(FREI_ABSORB, T_hist=hist_dev[1])
-            hist_dev[2].copy_(eng.dT)
-            hist_host.copy_(hist_dev, non_blocking=True)
-            torch.cuda.current_stream(eng.device).synchronize()
-            h = hist_host.numpy()
-            temp_hists.append(np.stack([h[0, 0], h[1, 0]], axis=1).copy())
-            dT = h[2, 0].copy()
+                eng.sweep(FREI_ABSORB, T_hist=eng.hist[1])
+            else:
+                eng.iteration()
+            T_emit, T_absorb, dT = eng.read_history()
+            temp_hists.append(np.stack([T_emit[0], T_absorb[0]], axis=1))
+            dT = dT[0]
             self.n_iterations += 1
             conv, _ = converged_layers(temp_hists, dT, n_zero_crossings, conv_dT)
             if np.all(conv):
@@ -266,16 +288,38 @@ class Grid(object):
             eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
         # final emit: alpha is not forwarded -> default 1 (frei/core.py:323-333)
         eng.sweep(FREI_EMIT, alpha_override=1.0, with_dtaus=True)
-        final_temps = eng.T[0].cpu().numpy()
         spec_local = eng.F_up[0, L - 1]
         dtaus_local = eng.dtaus[0]
         if group is not None:
+            final_temps = eng.T[0].cpu().numpy()
             spec, dtaus = _gather_lambda(spec_local, dtaus_local, eng, group)
         else:
-            spec, dtaus = spec_local.cpu().numpy(), dtaus_local.cpu().numpy()
+            out = self._outputs.get((L + 1, eng.n_lam))        # pinned: [0] spectrum, [1:] dtaus
+            out[0].copy_(spec_local, non_blocking=True)
+            out[1:].copy_(dtaus_local, non_blocking=True)
+            final_temps = eng.T[0].cpu().numpy()               # synchronises the stream
+            arr = self._outputs.hand_out(out)
+            spec, dtaus = arr[0], arr[1:]
         self.engine = eng
         return (_make_spectrum(U.wrap(spec, 'flux'), self.lam), U.wrap(final_temps, 'K'),
                 U.wrap(temp_hist, 'K'), dtaus)
+
+    def _solver_engine(self, group):
+        """Device state of this Grid, built once and reset for every solve."""
+        pl = self.planet
+        T0 = U.value(self.init_temperatures, 'K')
+        P = U.value(self.pressures, 'bar')
+        m_bar_g = float(U.value(pl.m_bar, 'g'))
+        table = self.device_table(group)
+        key = (id(table), id(group), T0.shape, U.value(self.lam, 'um').shape,
+               U.gravity_cgs(pl.g), m_bar_g, float(pl.alpha), float(U.value(pl.T_star, 'K')),
+               float(pl.a_rstar), P.tobytes())
+        if getattr(self, '_eng_key', None) != key:
+            self._eng = self.make_engine(group=group, want_dtaus=True)
+            self._eng_key = key
+        else:
+            self._eng.reset(T0, self._mmr(T0, P, m_bar_g))
+        return self._eng
 
     def emission_dashboard(self, *args, **kwargs):
         raise NotImplementedError('plotting is outside the scope of frei_b200 (frei/plot.py)')

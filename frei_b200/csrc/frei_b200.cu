@@ -58,7 +58,7 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
 constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxS = 32;
-constexpr int kPostChunks = 64;         // stage-1 CTAs of the partials reduction
+constexpr int kPostChunks = 148;        // stage-1 CTAs of the partials reduction (one per SM)
 
 // ---------------------------------------------------------------------------
 // workspace layout
@@ -857,29 +857,46 @@ struct PostArgs {
     int do_update, do_prep;
 };
 
+// Sum `count` rows of n doubles (row stride n) element-wise with all threads of the CTA:
+// thread (g, e) adds rows g, g + G, ... of element e (independent loads), then the G group
+// results are added in group order through shared memory.  Fixed order -> deterministic.
+__device__ __forceinline__ double cta_column_sum(const double* __restrict__ rows, int count, int n,
+                                                 double* scratch /* [G][n] */, int G) {
+    const int e = threadIdx.x % n, g = threadIdx.x / n;
+    double s = 0.0;
+    if (g < G) {
+#pragma unroll 4
+        for (int r = g; r < count; r += G) s += rows[(int64_t)r * n + e];
+        scratch[g * n + e] = s;
+    }
+    __syncthreads();
+    double tot = 0.0;
+    if (g == 0)
+        for (int k = 0; k < G; ++k) tot += scratch[k * n + e];
+    __syncthreads();
+    return tot;              // valid in threads with g == 0 (threadIdx.x < n)
+}
+
 __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
-    extern __shared__ double sm_sums[];          // [L][4]
+    extern __shared__ double sm_post[];          // [G][n] scratch, then [n] sums
     __shared__ int is_last;
     const int b = blockIdx.y, chunk = blockIdx.x, n = u.L * 4;
+    const int G = blockDim.x / n;                // row groups per CTA (>= 1, host guarantees)
+    double* sm_sums = sm_post + (size_t)G * n;
     const int r0 = chunk * q.rows_per_chunk, r1 = min(q.rows, r0 + q.rows_per_chunk);
-    const double* p = q.partials + (int64_t)b * q.rows * n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        double s = 0.0;
-        for (int r = r0; r < r1; ++r) s += p[(int64_t)r * n + e];
-        q.chunk_sums[((int64_t)b * q.nchunks + chunk) * n + e] = s;
-    }
+    const double* p = q.partials + ((int64_t)b * q.rows + r0) * n;
+    const double s1 = cta_column_sum(p, r1 - r0, n, sm_post, G);
+    if (threadIdx.x < n) q.chunk_sums[((int64_t)b * q.nchunks + chunk) * n + threadIdx.x] = s1;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(q.counters + b, 1u) == (unsigned)(q.nchunks - 1));
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const double* cs = q.chunk_sums + (int64_t)b * q.nchunks * n;
-    for (int e = threadIdx.x; e < n; e += blockDim.x) {
-        double s = 0.0;
-        for (int c = 0; c < q.nchunks; ++c) s += cs[(int64_t)c * n + e];
-        q.sums[(int64_t)b * n + e] = s;
-        sm_sums[e] = s;
+    const double s2 = cta_column_sum(q.chunk_sums + (int64_t)b * q.nchunks * n, q.nchunks, n, sm_post, G);
+    if (threadIdx.x < n) {
+        q.sums[(int64_t)b * n + threadIdx.x] = s2;
+        sm_sums[threadIdx.x] = s2;
     }
     if (threadIdx.x == 0) q.counters[b] = 0u;    // self-cleaning for the next launch
     if (!q.do_update) return;
@@ -1104,7 +1121,7 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
                        int64_t n_lam, int do_update, int do_prep, int direction,
                        double alpha_override, double* d_T_hist, cudaStream_t st) {
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
-    ARG_TRY(atm->L >= 3 && atm->L <= 1024 && atm->B <= 65535);
+    ARG_TRY(atm->L >= 3 && atm->L <= 256 && atm->B <= 65535);
     PostArgs q;
     q.rows = (int)sweep_blocks(n_lam) * kWarps;
     q.nchunks = q.rows < kPostChunks ? q.rows : kPostChunks;
@@ -1130,9 +1147,12 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
         if (rc) return rc;
         fill_prep(pa, tab, atm, ws);
     }
-    int threads = ((atm->L + 31) / 32) * 32;
-    if (threads < 256) threads = 256;
-    post_kernel<<<dim3(q.nchunks, atm->B), threads, (size_t)n * sizeof(double), st>>>(q, u, pa);
+    // threads = G row groups x n columns, at least L (update) and n = 4 L (columns)
+    int G = 1024 / (int)n;
+    if (G < 1) return set_err(FREI_E_UNSUPPORTED, "more than 256 levels%s%s");
+    if (G > 8) G = 8;
+    const int threads = (G * (int)n + 31) / 32 * 32;
+    post_kernel<<<dim3(q.nchunks, atm->B), threads, (size_t)(G + 1) * n * sizeof(double), st>>>(q, u, pa);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }

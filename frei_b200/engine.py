@@ -201,9 +201,14 @@ class Engine:
         self._lp = torch.empty(sizes[0].value, dtype=torch.uint8, device=dev)
         self._partials = torch.zeros((sizes[1].value + 7) // 8, dtype=f64, device=dev)   # incl. ticket counters
         self.sums = torch.zeros((B, L, 4), dtype=f64, device=dev)
-        self.dT = torch.zeros((B, L), dtype=f64, device=dev)
+        # [0] = T after the last emit, [1] = T after the last absorb, [2] = dT of the last sweep:
+        # one small D2H copy per iteration brings back everything the host convergence test needs
+        self.hist = torch.zeros((3, B, L), dtype=f64, device=dev)
+        self.dT = self.hist[2]
+        self._hist_host = None
         self.launches = 0
         self._records_stale = True     # level records must be rebuilt before the next sweep
+        self._graph = None
         self.sweep_events = None        # list of (start, end) CUDA events around the sweep kernel
         self._build_structs()
 
@@ -251,6 +256,61 @@ class Engine:
 
     def get_T(self):
         return self.T.cpu().numpy()
+
+    def reset(self, temperatures, mmr=None):
+        """Back to the initial state of a solve: zero fluxes (frei/core.py:265-266), given T."""
+        self.F_up.zero_()
+        self.F_down.zero_()
+        self.set_T(temperatures)
+        if mmr is not None:
+            self.set_mmr(mmr)
+
+    def iteration(self):
+        """emit + absorb (one pass of the loop body of frei/core.py:273-299), asynchronous."""
+        if self._graph is not None and not self._records_stale and self.sweep_events is None:
+            self._graph.replay()
+            self.launches += 4
+            return
+        self.sweep(FREI_EMIT, T_hist=self.hist[0])
+        self.sweep(FREI_ABSORB, T_hist=self.hist[1])
+
+    def capture_iteration(self):
+        """
+        Record emit + absorb (4 kernel launches on one device) into a CUDA graph so that an
+        iteration is one graph launch.  Single-device engines only; the state the graph reads
+        and writes (T, fluxes, records, hist) keeps its addresses for the life of the engine.
+        """
+        torch = _torch()
+        if self.group is not None:
+            return False
+        if self._records_stale:
+            self.layer_prep()
+        # the captured launches run for real once during warm-up below; keep the state intact
+        keep = [t.clone() for t in (self.T, self.F_up, self.F_down, self.hist, self._lp)]
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            self.sweep(FREI_EMIT, T_hist=self.hist[0])      # warm-up outside capture (attribute calls)
+            self.sweep(FREI_ABSORB, T_hist=self.hist[1])
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.sweep(FREI_EMIT, T_hist=self.hist[0])
+            self.sweep(FREI_ABSORB, T_hist=self.hist[1])
+        for dst, src in zip((self.T, self.F_up, self.F_down, self.hist, self._lp), keep):
+            dst.copy_(src)
+        self._graph = graph
+        return True
+
+    def read_history(self):
+        """(T after emit, T after absorb, dT of the absorb sweep) as host arrays [B][L]; syncs."""
+        torch = _torch()
+        if self._hist_host is None:
+            self._hist_host = torch.empty((3, self.B, self.L), dtype=torch.float64).pin_memory()
+        self._hist_host.copy_(self.hist, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        h = self._hist_host.numpy()
+        return h[0].copy(), h[1].copy(), h[2].copy()
 
     # -- kernels ------------------------------------------------------------
     def layer_prep(self, debug=False):
