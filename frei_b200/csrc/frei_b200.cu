@@ -53,7 +53,10 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
 #define SWEEP_THREADS 128
 #endif
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 4
+#define SWEEP_MINB 4              // resident CTAs per SM the V = 2 sweep kernel is compiled for
+#endif
+#ifndef SWEEP_MINB_V1
+#define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
 #endif
 constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
@@ -87,7 +90,7 @@ static inline LayerParams layer_params_view(void* p, int S) {
     return v;
 }
 static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
-static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + kWarps; }   // warps at V = 1
+static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + 2 * kWarps; }   // bound on the plan's rows
 
 // ---------------------------------------------------------------------------
 // K0: brackets, weights, per-layer scalars
@@ -409,8 +412,10 @@ struct SweepArgs {
     const double* sigma_scale; const double* ftoa_scale;
     LayerParams lp;
     void* F_up; void* F_down; void* dtaus;
-    double* partials;           // [B][gridDim.x * kWarps][L][4]
+    double* partials;           // [B][rows][L][4], one row per sweep warp
     int64_t n_lam;
+    int64_t j0, j1;             // wavelength range [j0, j1) covered by this launch
+    int row0, rows;             // first partial row of this launch, total rows of the sweep
     int B, L, S, N_T;
 };
 
@@ -614,7 +619,7 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 // and both are written back.  The level records are staged into shared memory by one TMA bulk
 // copy.  The loop body is a single basic block (no data-dependent or uniform branches).
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-__global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double tab[32];                   // 2^(j/32) for exp_neg
@@ -625,7 +630,7 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
     double* sm_rec = smem;                       // [L][rec8]
     const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
     // this warp's wavelength-integral partials: partials[b][cta * kWarps + warp][L][4]
-    double* part = a.partials + (((int64_t)b * gridDim.x + blockIdx.x) * kWarps + warp) * L * 4;
+    double* part = a.partials + ((int64_t)b * a.rows + a.row0 + blockIdx.x * kWarps + warp) * L * 4;
     const uint32_t stage = smem_u32(slot);       // [4 S][kThreads][V] staged table elements
     const int64_t n_lam = a.n_lam;
 
@@ -645,9 +650,9 @@ __global__ void __launch_bounds__(kThreads, SWEEP_MINB) sweep_kernel(SweepArgs a
     }
 
     // ---- per-wavelength constants (overlaps the copy) ----
-    const int64_t j_raw = ((int64_t)blockIdx.x * kThreads + tid) * V;
-    const bool live = j_raw < n_lam;             // n_lam % V == 0, so all V lanes are in range
-    const int64_t j = live ? j_raw : n_lam - V;
+    const int64_t j_raw = a.j0 + ((int64_t)blockIdx.x * kThreads + tid) * V;
+    const bool live = j_raw < a.j1;              // (j1 - j0) % V == 0, so all V lanes are in range
+    const int64_t j = live ? j_raw : a.j1 - V;
     const TabT* tabj = static_cast<const TabT*>(a.tab) + j;
     const int64_t rowT = (int64_t)a.N_T * n_lam;
     double* Fu = static_cast<double*>(a.F_up) + (int64_t)b * L * n_lam + j;
@@ -907,18 +912,56 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
 // ---------------------------------------------------------------------------
 // host side of the ABI
 // ---------------------------------------------------------------------------
-#ifndef SWEEP_V
-#define SWEEP_V 2                 // wavelengths per thread when n_lam allows (experiment knob: 1, 2, 4)
+// ---- launch plan -------------------------------------------------------------------------------
+// A sweep is one launch of V = 2 CTAs (256 wavelengths each; V = 1 for odd wavelength counts).
+// Every column is a serial recurrence over the layers, so a partly filled last wave of CTAs costs
+// nearly as much as a full one.  -DSWEEP_TAIL_SPLIT hands the wavelengths of such a wave to V = 1
+// CTAs (128 wavelengths, 78 registers) launched right behind the main part; on B200 this measured
+// no faster, so it is off by default.  DESIGN.md 3.1 / 7.
+struct SweepPlan {
+    int nparts;
+    struct { int V; int64_t j0, j1; int row0; unsigned blocks; } part[2];
+    int rows;
+};
+
+static int g_num_sms = 0;
+static int num_sms() {
+    if (g_num_sms == 0) {
+        int dev = 0, n = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess &&
+            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+            g_num_sms = n;
+        else
+            g_num_sms = 148;
+    }
+    return g_num_sms;
+}
+
+static SweepPlan make_plan(int64_t n_lam, int B) {
+    SweepPlan p{};
+    auto add = [&](int V, int64_t j0, int64_t j1) {
+        auto& q = p.part[p.nparts++];
+        q.V = V; q.j0 = j0; q.j1 = j1; q.row0 = p.rows;
+        q.blocks = (unsigned)((j1 - j0 + (int64_t)kThreads * V - 1) / ((int64_t)kThreads * V));
+        p.rows += (int)q.blocks * kWarps;
+    };
+    if (n_lam % 2 != 0) { add(1, 0, n_lam); return p; }
+    const int64_t per_cta = (int64_t)kThreads * 2;
+    const int64_t ctas = (n_lam + per_cta - 1) / per_cta;
+    const int64_t wave = (int64_t)num_sms() * SWEEP_MINB / (B < 1 ? 1 : B);   // CTAs of one wave per atmosphere
+    const int64_t full = wave > 0 ? ctas / wave : 0, rest = wave > 0 ? ctas % wave : 0;
+#ifdef SWEEP_TAIL_SPLIT   // measured on B200: no gain (a column costs ~49 x 1500 cycles of latency at any V)
+    if (wave > 0 && full >= 1 && full < 4 && rest > 0 && rest * 10 < wave * 7) {
+        const int64_t j_split = full * wave * per_cta;
+        add(2, 0, j_split);
+        add(1, j_split, n_lam);
+        return p;
+    }
 #endif
-static inline int sweep_V(int64_t n_lam) {
-    if (SWEEP_V == 4 && n_lam % 4 == 0) return 4;
-    if (SWEEP_V >= 2 && n_lam % 2 == 0) return 2;
-    return 1;
+    add(2, 0, n_lam);
+    return p;
 }
-static inline int64_t sweep_blocks(int64_t n_lam) {
-    const int64_t per = (int64_t)kThreads * sweep_V(n_lam);
-    return (n_lam + per - 1) / per;
-}
+static inline int sweep_rows(int64_t n_lam, int B) { return make_plan(n_lam, B).rows; }
 
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
 static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
@@ -934,11 +977,6 @@ static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStre
 
 template <typename TabT, int S_T, int DIR>
 static int launch_sweep_v(const SweepArgs& a, int V, dim3 grid, size_t smem, cudaStream_t st) {
-#if SWEEP_V == 4
-    if (V == 4)
-        return a.dtaus ? launch_sweep_one<TabT, S_T, DIR, 4, true>(a, grid, smem, st)
-                       : launch_sweep_one<TabT, S_T, DIR, 4, false>(a, grid, smem, st);
-#endif
     if (a.dtaus)
         return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, grid, smem, st)
                       : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, grid, smem, st);
@@ -1086,17 +1124,25 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.F_up = flux->F_up; a.F_down = flux->F_down; a.dtaus = flux->dtaus;
     a.partials = ws->partials;
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
-    const int V = sweep_V(tab->n_lam);
-    dim3 grid((unsigned)sweep_blocks(tab->n_lam), atm->B);
+    const SweepPlan plan = make_plan(tab->n_lam, atm->B);
+    a.rows = plan.rows;
+    for (int ip = 0; ip < plan.nparts; ++ip) {
+        const int V = plan.part[ip].V;
+        a.j0 = plan.part[ip].j0; a.j1 = plan.part[ip].j1; a.row0 = plan.part[ip].row0;
+        dim3 grid(plan.part[ip].blocks, atm->B);
 #ifndef SWEEP_SMEM_PAD
 #define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
 #endif
-    const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
-                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
-    if (smem > 200 * 1024)
-        return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
-    if (tab->dtype == FREI_F32) return launch_sweep<float>(a, direction, V, grid, smem, (cudaStream_t)stream);
-    return launch_sweep<double>(a, direction, V, grid, smem, (cudaStream_t)stream);
+        const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
+                            (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
+        if (smem > 200 * 1024)
+            return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
+        rc = (tab->dtype == FREI_F32)
+                 ? launch_sweep<float>(a, direction, V, grid, smem, (cudaStream_t)stream)
+                 : launch_sweep<double>(a, direction, V, grid, smem, (cudaStream_t)stream);
+        if (rc) return rc;
+    }
+    return FREI_OK;
 }
 
 static void fill_prep(PrepArgs& a, const frei_table* tab, const frei_atmosphere* atm,
@@ -1123,7 +1169,7 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
     ARG_TRY(atm->L >= 3 && atm->L <= 256 && atm->B <= 65535);
     PostArgs q;
-    q.rows = (int)sweep_blocks(n_lam) * kWarps;
+    q.rows = sweep_rows(n_lam, atm->B);
     q.nchunks = q.rows < kPostChunks ? q.rows : kPostChunks;
     q.rows_per_chunk = (q.rows + q.nchunks - 1) / q.nchunks;
     q.nchunks = (q.rows + q.rows_per_chunk - 1) / q.rows_per_chunk;
