@@ -15,12 +15,14 @@ checkout).  The (P, T) interpolation calls ``scipy.interpolate.interpn`` /
 in ``frei/opacity.py:261-263`` — so that step is the reference's own
 arithmetic, not a restatement.
 
-Pinning: the oracle is checked in ``tests/test_oracle.py`` against every
-known-answer value the reference's tests hold for this path
-(``frei/tests/test_core.py:42,44,52-56,60-64,67-71``) and against the golden
-vectors in ``tests/golden`` (generated by running the reference's own
-``twostream.py`` / ``opacity.py`` / ``core.py`` sources under dependency stubs,
-see ``tests/golden/make_golden.py``).
+Pinning (``tests/test_oracle.py``): (1) every known-answer value the reference's
+tests hold for this path (``frei/tests/test_core.py:42,44,52-56,60-64,67-71``);
+(2) ``tests/golden/reference_run.json`` — outputs of the reference's OWN source
+files (``frei/twostream.py``, ``opacity.py``, ``core.py``, ``tp.py``,
+``chemistry.py``) executed here under dependency stubs for astropy.units, xarray,
+specutils and periodictable (``tests/golden/run_reference.py``, ``refstubs/``):
+kappa, one-step and fully converged ``emission_spectrum``, ``propagate_fluxes``,
+the layer thermodynamics and the mock chemistry agree to 1e-9 .. 1e-13.
 
 Conventions: layer index 0 = bottom (highest pressure) (``frei/tp.py:32``);
 wavelength ascending.  Pressures are carried in bar where the reference does

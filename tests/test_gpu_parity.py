@@ -482,3 +482,44 @@ def test_full_size_sampled_parity_and_integrals():
         else:
             np.testing.assert_allclose(sums[1:L - 1, 1], (Fd_before[2:L] * wts).sum(axis=1), rtol=1e-11)
         T = eng.T[0].cpu().numpy()      # continue the oracle from the GPU's T (global integrals)
+
+
+def test_gpu_vs_reference_own_run():
+    """
+    The GPU path through the mirrored API against tests/golden/reference_run.json — outputs of
+    the reference's OWN source files run under dependency stubs (tests/golden/run_reference.py).
+    """
+    import json
+    import os
+    import frei_b200 as frei
+    with open(os.path.join(os.path.dirname(__file__), 'golden', 'reference_run.json')) as fh:
+        ref = json.load(fh)
+    a = ref['A']
+    planet = frei.Planet.from_hot_jupiter()
+    grid = frei.Grid(planet=planet, T_ref=2400)
+    op = grid.load_opacities(opacities=frei.load_example_opacity(grid, scale_factor=1))
+    idx = a['lam_index']
+    k, sigma = frei.kappa(op, grid.init_temperatures[0], grid.pressures[0], grid.lam, m_bar=planet.m_bar)
+    np.testing.assert_allclose(np.asarray(k)[idx], a['kappa0'], rtol=1e-12)
+    np.testing.assert_allclose(np.asarray(sigma)[idx], a['sigma'], rtol=1e-11)
+    spec, temps, hist, dtaus = grid.emission_spectrum(n_timesteps=1)
+    # 1e-6 is the contract; the reference's own fp64 noise in thin layers is ~1e-9 here
+    np.testing.assert_allclose(np.asarray(spec.flux)[idx], a['spectrum'], rtol=1e-8)
+    np.testing.assert_allclose(temps, a['final_temps'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(hist, a['temp_hist'], rtol=0, atol=1e-5)
+    np.testing.assert_allclose(dtaus[:, idx], a['dtaus'], rtol=1e-11)
+    assert abs(frei.effective_temperature(grid, spec, dtaus, temps) - a['T_eff']) < 1e-4
+    # full solve on the small grid: same number of iterations, converged T within 0.1 K (contract)
+    b = ref['B']
+    grid = frei.Grid(planet=planet, T_ref=2400, n_layers=12, n_wl_bins=120)
+    grid.load_opacities(opacities=frei.load_example_opacity(grid, scale_factor=1))
+    spec, temps, hist, dtaus = grid.emission_spectrum(n_timesteps=400)
+    assert hist.shape[1] == b['n_columns']
+    assert np.abs(np.asarray(temps) - np.array(b['final_temps'])).max() < 1e-3
+    np.testing.assert_allclose(np.asarray(spec.flux), b['spectrum'], rtol=1e-6)
+    # propagate_fluxes, both E branches
+    c = ref['C']
+    F2u, F1d = frei.propagate_fluxes(np.array(c['lam_um']), np.array(c['F1']), np.array(c['F2']),
+                                     1800.0, 1650.0, np.array(c['dtau']), omega_0=np.array(c['w0']), g_0=0)
+    np.testing.assert_allclose(F2u, c['F2u'], rtol=1e-9)
+    np.testing.assert_allclose(F1d, c['F1d'], rtol=1e-9)
