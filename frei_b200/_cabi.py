@@ -32,10 +32,17 @@ class frei_spectral(C.Structure):
                 ('f_toa', c_void_p), ('n_lam', c_int64)]
 
 
+class frei_tracker(C.Structure):
+    _fields_ = [('last_T', c_void_p), ('state', c_void_p), ('n_columns', c_void_p),
+                ('iterations', c_void_p), ('n_zero_crossings', c_int32),
+                ('convergence_dT', c_double)]
+
+
 class frei_atmosphere(C.Structure):
     _fields_ = [('T', c_void_p), ('P', c_void_p), ('mmr', c_void_p), ('g', c_void_p),
                 ('m_bar', c_void_p), ('alpha', c_void_p), ('sigma_scale', c_void_p),
-                ('ftoa_scale', c_void_p), ('B', c_int32), ('L', c_int32)]
+                ('ftoa_scale', c_void_p), ('B', c_int32), ('L', c_int32),
+                ('active', c_void_p), ('tracker', C.POINTER(frei_tracker))]
 
 
 class frei_flux(C.Structure):

@@ -410,6 +410,7 @@ struct SweepArgs {
     const void* tab;
     const double* c1; const double* c2; const double* sigma; const double* w; const double* f_toa;
     const double* sigma_scale; const double* ftoa_scale;
+    const uint8_t* active;      // [B] or null: atmospheres with 0 are skipped (batch convergence)
     LayerParams lp;
     void* F_up; void* F_down; void* dtaus;
     double* partials;           // [B][rows][L][4], one row per sweep warp
@@ -625,6 +626,7 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     __shared__ double tab[32];                   // 2^(j/32) for exp_neg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
+    if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
     if (tid < 32) tab[tid] = kExp2Tab[tid];
     double* sm_rec = smem;                       // [L][rec8]
@@ -786,6 +788,14 @@ struct UpdateArgs {
     double* dT; double* T_hist;
     int L, direction;
     double alpha_override;
+    // batch convergence (core.py:301-318), all nullable
+    uint8_t* active;            // [B] in/out
+    double* trk_T;              // [B][L] temperature in the previous history column
+    int32_t* trk_state;         // [B][L][2] sign of the previous difference (2 = none yet), sign flips
+    int32_t* trk_ncol;          // [B] history columns so far
+    int32_t* trk_iters;         // [B] emit+absorb iterations done when the atmosphere converged
+    int n_zero_crossings;
+    double convergence_dT;
 };
 
 // dT of level i of atmosphere b from its four wavelength integrals s[0..3]
@@ -834,11 +844,42 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
         dT = delta_T_level(u, b, i, sums_b + i * 4);
     }
     __syncthreads();
+    const double Tn = T1 - dT;                                                // :407, :536
     if (i < L) {
-        const double Tn = T1 - dT;                                            // :407, :536
         u.dT[(int64_t)b * L + i] = dT;
         u.T[(int64_t)b * L + i] = Tn;
         if (u.T_hist) u.T_hist[(int64_t)b * L + i] = Tn;
+    }
+    if (u.trk_T) {
+        // Per-layer convergence of Grid.emission_spectrum (core.py:306-311), kept incrementally:
+        // every sweep appends a history column; a layer is converged when the successive column
+        // differences changed sign more than n_zero_crossings times, or the absorb step is below
+        // convergence_dT; the atmosphere stops when all layers are (tested after absorb, :317).
+        bool conv = true;
+        if (i < L) {
+            const int64_t li = (int64_t)b * L + i;
+            const int ncol = u.trk_ncol[b];
+            int sgn_prev = u.trk_state[li * 2], flips = u.trk_state[li * 2 + 1];
+            if (ncol > 0) {
+                const double d = Tn - u.trk_T[li];
+                const int sgn = (d > 0.0) - (d < 0.0);
+                if (sgn_prev != 2 && sgn != sgn_prev) ++flips;
+                sgn_prev = sgn;
+            }
+            u.trk_T[li] = Tn;
+            u.trk_state[li * 2] = sgn_prev;
+            u.trk_state[li * 2 + 1] = flips;
+            conv = (flips > u.n_zero_crossings) || (fabs(dT) < u.convergence_dT);
+        }
+        const int all_conv = __syncthreads_and(conv ? 1 : 0);
+        if (i == 0) {
+            const int ncol = u.trk_ncol[b] + 1;
+            u.trk_ncol[b] = ncol;
+            if (u.direction == FREI_ABSORB && all_conv && u.active) {
+                u.active[b] = 0;
+                if (u.trk_iters) u.trk_iters[b] = ncol / 2;
+            }
+        }
     }
     if (!do_prep) return;
     __syncthreads();
@@ -846,6 +887,7 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
 }
 
 __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums) {
+    if (u.active && !u.active[blockIdx.x]) return;
     update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4);
 }
 
@@ -858,6 +900,7 @@ __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const
 // and rebuild the level records, so one launch follows each sweep.
 struct PostArgs {
     const double* partials; double* chunk_sums; unsigned int* counters; double* sums;
+    const uint8_t* active;
     int rows, rows_per_chunk, nchunks;
     int do_update, do_prep;
 };
@@ -886,6 +929,7 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
     extern __shared__ double sm_post[];          // [G][n] scratch, then [n] sums
     __shared__ int is_last;
     const int b = blockIdx.y, chunk = blockIdx.x, n = u.L * 4;
+    if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
     const int G = blockDim.x / n;                // row groups per CTA (>= 1, host guarantees)
     double* sm_sums = sm_post + (size_t)G * n;
     const int r0 = chunk * q.rows_per_chunk, r1 = min(q.rows, r0 + q.rows_per_chunk);
@@ -1119,7 +1163,7 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     SweepArgs a;
     a.tab = tab->values;
     a.c1 = spec->c1; a.c2 = spec->c2; a.sigma = spec->sigma; a.w = spec->w; a.f_toa = spec->f_toa;
-    a.sigma_scale = atm->sigma_scale; a.ftoa_scale = atm->ftoa_scale;
+    a.sigma_scale = atm->sigma_scale; a.ftoa_scale = atm->ftoa_scale; a.active = atm->active;
     a.lp = layer_params_view(ws->layer_params, tab->S);
     a.F_up = flux->F_up; a.F_down = flux->F_down; a.dtaus = flux->dtaus;
     a.partials = ws->partials;
@@ -1160,6 +1204,14 @@ static void fill_update(UpdateArgs& u, const frei_atmosphere* atm, const frei_wo
     u.T = atm->T; u.P = atm->P; u.g = atm->g; u.m_bar = atm->m_bar; u.alpha = atm->alpha;
     u.dT = ws->dT; u.T_hist = d_T_hist;
     u.L = atm->L; u.direction = direction; u.alpha_override = alpha_override;
+    u.active = atm->active;
+    const frei_tracker* t = atm->tracker;
+    u.trk_T = t ? t->last_T : nullptr;
+    u.trk_state = t ? t->state : nullptr;
+    u.trk_ncol = t ? t->n_columns : nullptr;
+    u.trk_iters = t ? t->iterations : nullptr;
+    u.n_zero_crossings = t ? t->n_zero_crossings : 0;
+    u.convergence_dT = t ? t->convergence_dT : 0.0;
 }
 
 // reduce (+ update T (+ rebuild records)) in one launch
@@ -1178,6 +1230,7 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     q.chunk_sums = ws->partials + (int64_t)atm->B * sweep_rows_max(n_lam) * n;
     q.counters = reinterpret_cast<unsigned int*>(q.chunk_sums + (int64_t)atm->B * kPostChunks * n);
     q.sums = ws->sums;
+    q.active = atm->active;
     q.do_update = do_update; q.do_prep = do_prep;
     UpdateArgs u{};
     PrepArgs pa{};

@@ -222,10 +222,12 @@ class Engine:
         self._spec = _cabi.frei_spectral(self.c1.data_ptr(), self.c2.data_ptr(),
                                          self.sigma.data_ptr(), self.w.data_ptr(),
                                          self.f_toa.data_ptr(), n)
+        trk = getattr(self, '_tracker', None)
         self._atm = _cabi.frei_atmosphere(
             self.T.data_ptr(), self.P.data_ptr(), self.mmr.data_ptr(), self.g.data_ptr(),
             self.m_bar.data_ptr(), self.alpha.data_ptr(), _cabi.ptr(self.sigma_scale),
-            _cabi.ptr(self.ftoa_scale), self.B, self.L)
+            _cabi.ptr(self.ftoa_scale), self.B, self.L,
+            _cabi.ptr(getattr(self, 'active', None)), C.pointer(trk) if trk is not None else None)
         self._ws = _cabi.frei_workspace(self._lp.data_ptr(), self._partials.data_ptr(),
                                         self.sums.data_ptr(), self.dT.data_ptr())
 
@@ -273,6 +275,53 @@ class Engine:
             return
         self.sweep(FREI_EMIT, T_hist=self.hist[0])
         self.sweep(FREI_ABSORB, T_hist=self.hist[1])
+
+    # -- batches of atmospheres: convergence decided on the device ---------------------------
+    def enable_batch_convergence(self, n_zero_crossings=2, convergence_dT=3.0):
+        """
+        Track the convergence rule of Grid.emission_spectrum (frei/core.py:301-318) per
+        atmosphere on the device; converged atmospheres are skipped by every later kernel.
+        """
+        torch = _torch()
+        dev, B, L = self.device, self.B, self.L
+        self.active = torch.ones(B, dtype=torch.uint8, device=dev)
+        self._trk_T = torch.zeros((B, L), dtype=torch.float64, device=dev)
+        self._trk_state = torch.zeros((B, L, 2), dtype=torch.int32, device=dev)
+        self._trk_state[:, :, 0] = 2
+        self._trk_ncol = torch.zeros(B, dtype=torch.int32, device=dev)
+        self.iterations_done = torch.zeros(B, dtype=torch.int32, device=dev)
+        self._tracker = _cabi.frei_tracker(self._trk_T.data_ptr(), self._trk_state.data_ptr(),
+                                           self._trk_ncol.data_ptr(),
+                                           self.iterations_done.data_ptr(), int(n_zero_crossings),
+                                           float(convergence_dT))
+        self._build_structs()
+
+    def disable_batch_convergence(self):
+        self.active = None
+        self._tracker = None
+        self._build_structs()
+
+    def solve_batch(self, n_timesteps, n_zero_crossings=2, convergence_dT=3.0, check_every=4):
+        """
+        Grid.emission_spectrum for every atmosphere of the batch (frei/core.py:263-333): iterate
+        emit/absorb until each atmosphere meets the convergence rule (or n_timesteps), then the
+        final emit with alpha = 1.  Returns (iterations[B], T[B][L]) as host arrays; the spectra
+        are F_up[:, L-1, :] on the device.  The host only polls the per-atmosphere flags every
+        ``check_every`` iterations.
+        """
+        self.enable_batch_convergence(n_zero_crossings, convergence_dT)
+        n_done = 0
+        for it in range(n_timesteps):
+            self.iteration()
+            n_done += 1
+            if (it + 1) % check_every == 0 and not bool(self.active.any().item()):
+                break
+        iters = self.iterations_done.cpu().numpy().copy()
+        still = self.active.cpu().numpy().astype(bool)
+        iters[still] = n_done                                  # stopped by n_timesteps
+        self.disable_batch_convergence()
+        self.sweep(FREI_EMIT, alpha_override=1.0)              # final emit, alpha not forwarded (:323-333)
+        return iters, self.T.cpu().numpy()
 
     def capture_iteration(self):
         """

@@ -75,6 +75,20 @@ typedef struct {
     int64_t       n_lam;
 } frei_spectral;
 
+/* Device-side convergence bookkeeping of a batch (optional): the rule of
+ * Grid.emission_spectrum (frei/core.py:301-318) evaluated incrementally after every sweep,
+ * so that a batch of atmospheres never synchronises with the host per atmosphere.
+ * All arrays are device memory, zero-initialised by the caller except state[..][0] = 2. */
+typedef struct {
+    double*  last_T;            /* [B][L] temperature in the previous history column        */
+    int32_t* state;             /* [B][L][2]: sign of the previous column difference (2 =
+                                   none yet), number of sign changes so far                  */
+    int32_t* n_columns;         /* [B] history columns so far (2 per iteration)              */
+    int32_t* iterations;        /* [B] or NULL: iterations done when the atmosphere converged */
+    int32_t  n_zero_crossings;  /* default 2, frei/core.py:233                               */
+    double   convergence_dT;    /* default 3 K                                               */
+} frei_tracker;
+
 /* B independent atmospheres of L levels each. */
 typedef struct {
     double*       T;            /* device [B][L], in/out                               */
@@ -87,6 +101,10 @@ typedef struct {
     const double* sigma_scale;  /* device [B] or NULL: sigma_b = sigma * scale_b       */
     const double* ftoa_scale;   /* device [B] or NULL: F_TOA_b = f_toa * scale_b       */
     int32_t       B, L;
+    uint8_t*      active;       /* device [B] or NULL: atmospheres whose flag is 0 are
+                                   skipped by every kernel; cleared by the tracker when
+                                   an atmosphere converges                              */
+    const frei_tracker* tracker;/* host pointer or NULL                                */
 } frei_atmosphere;
 
 /* Flux state, mutated in place like the reference's fluxes_up / fluxes_down

@@ -29,7 +29,8 @@ def test_every_declared_symbol_is_exported_and_bound():
 def test_struct_layouts_match_header():
     assert C.sizeof(_cabi.frei_table) == 4 * 8 + 4 * 4 + 8
     assert C.sizeof(_cabi.frei_spectral) == 5 * 8 + 8
-    assert C.sizeof(_cabi.frei_atmosphere) == 8 * 8 + 2 * 4
+    assert C.sizeof(_cabi.frei_atmosphere) == 8 * 8 + 2 * 4 + 2 * 8
+    assert C.sizeof(_cabi.frei_tracker) == 4 * 8 + 4 + 4 + 8
     assert C.sizeof(_cabi.frei_flux) == 3 * 8 + 8
     assert C.sizeof(_cabi.frei_workspace) == 4 * 8
 

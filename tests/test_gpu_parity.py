@@ -523,3 +523,37 @@ def test_gpu_vs_reference_own_run():
                                      1800.0, 1650.0, np.array(c['dtau']), omega_0=np.array(c['w0']), g_0=0)
     np.testing.assert_allclose(F2u, c['F2u'], rtol=1e-9)
     np.testing.assert_allclose(F1d, c['F1d'], rtol=1e-9)
+
+
+def test_batch_solve_device_convergence_matches_per_atmosphere_oracle():
+    """
+    A batch of different atmospheres (T profile, gravity, irradiation, abundances) solved in
+    lock-step with the convergence rule evaluated on the device: every atmosphere must stop after
+    the same number of iterations as the oracle's Grid.emission_spectrum and end at the same T.
+    """
+    from frei_b200 import synthetic
+    from frei_b200.engine import Engine, FREI_F64
+    L, n_lam, S = 14, 600, 3
+    w = synthetic.make_workload(L, n_lam, S)
+    tab = synthetic.device_table(w, FREI_F64)
+    tabs = synthetic.host_tables(w)
+    pl = w['planet']
+    B = 5
+    rs = np.random.RandomState(4)
+    T0 = w['T_init'][None, :] * np.array([0.6, 0.8, 1.0, 1.1, 0.9])[:, None]
+    g = pl['g'] * np.array([0.5, 1.0, 2.0, 4.0, 1.5])
+    a_rstar = pl['a_rstar'] * np.array([0.8, 1.0, 1.5, 2.5, 1.2])
+    mm = w['mmr'][None] * np.array([0.1, 1.0, 10.0, 3.0, 0.3])[:, None, None]
+    eng = Engine(tab, w['lam_um'], np.broadcast_to(w['P_bar'], (B, L)), T0, mm, g=g,
+                 m_bar=pl['m_bar'], alpha=1.0, T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+                 ftoa_scale=(pl['a_rstar'] / a_rstar) ** 2)
+    iters, T = eng.solve_batch(300, check_every=3)
+    spec = eng.F_up[:, L - 1, :].cpu().numpy()
+    assert len(set(iters.tolist())) > 1                        # they really stop at different times
+    for b in range(B):
+        planet = dict(pl, g=g[b], a_rstar=a_rstar[b])
+        s_ref, T_ref, hist, dtaus, n_it = O.emission_spectrum(
+            tabs, T0[b], w['P_bar'], w['lam_um'], planet, lambda x, y, m=mm[b, 0]: m, n_timesteps=300)
+        assert iters[b] == n_it, (b, iters[b], n_it)
+        assert np.abs(T[b] - T_ref).max() < 1e-3
+        assert _rel(spec[b], s_ref).max() < 1e-6
