@@ -35,6 +35,17 @@ METRIC = 'layer-lambda-bin two-stream flux evaluations/s'
 UNIT = 'evals/s'
 L_C2, NLAM_C2, S_C2, TREF_C2 = 50, 200_000, 3, 2400.0
 
+# BASELINE.json configs: name -> (layers, wavelength bins, species, T_ref, scaling, text)
+WORKLOADS = {
+    'C2': (50, 200_000, 3, 2400.0, 'weak', 'C2: hot Jupiter, 50 layers x 200k lambda bins per GPU, 3 species '
+           '(H2O+CO+CH4 synthetic tables), one RE iteration (emit+absorb) per step'),
+    'C1': (50, 5_000, 3, 2400.0, 'weak', 'C1: hot Jupiter, 50 layers x 5k lambda bins, 3 species, one RE iteration per step'),
+    'C3': (100, 1_000_000, 8, 3200.0, 'strong', 'C3: ultra-hot Jupiter, 100 layers x 1M lambda bins (global), '
+           '8 species, lambda-sharded, one RE iteration per step'),
+    'C5': (200, 2_000_000, 3, 2400.0, 'strong', 'C5: stress, 200 layers x 2M lambda bins (global), 3 species, '
+           'fp64, lambda-sharded, one RE iteration per step'),
+}
+
 
 def read_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
@@ -173,10 +184,10 @@ def run_ours(args):
     if args.gpus != world and rank == 0:
         print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
 
-    L, S = L_C2, S_C2
-    n_lam_global = NLAM_C2 * world                         # weak scaling: 200k bins per GPU
+    L, n_lam_w, S, T_ref, scaling, wl_text = WORKLOADS[args.workload]
+    n_lam_global = n_lam_w * world if scaling == 'weak' else n_lam_w   # weak: bins per GPU fixed
     tdtype = FREI_F32 if args.table_dtype == 32 else FREI_F64
-    w = synthetic.make_workload(L, n_lam_global, S, TREF_C2, table_f32=(tdtype == FREI_F32))
+    w = synthetic.make_workload(L, n_lam_global, S, T_ref, table_f32=(tdtype == FREI_F32))
     lo, hi = shard_range(n_lam_global, rank, world)
     table = synthetic.device_table(w, tdtype, lam_range=(lo, hi), device=dev)
     pl = w['planet']
@@ -260,22 +271,26 @@ def run_ours(args):
         e2e = {'value': None, 'error': repr(exc)}
 
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == 'C2':
         cpu = cpu_baseline_one_core()
 
     if rank == 0:
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
             'config': {
-                'workload': ('C2: hot Jupiter, 50 layers x 200k lambda bins per GPU, 3 species '
-                             '(H2O+CO+CH4 synthetic tables), one RE iteration (emit+absorb) per step'),
+                'workload': wl_text,
                 'n_layers': L, 'n_lambda_global': n_lam_global, 'n_species': S,
                 'table_dtype': f'f{args.table_dtype}', 'flux_dtype': 'f64',
                 'parallelism': f'lambda-sharded x{world}' if world > 1 else 'single GPU',
-                'l2': 'inputs larger than L2: flux state 160 MB + table '
-                      f'{table.values.numel() * b_tab / 1e6:.0f} MB per GPU touched every step',
+                'l2': 'inputs larger than L2: flux state '
+                      f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB + table '
+                      f'{table.values.numel() * b_tab / 1e6:.0f} MB per GPU touched every step'
+                      if 2 * L * (hi - lo) * 8 > 130e6 else
+                      'working set fits L2 (flux state '
+                      f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB): 256 MB scratch written between steps '
+                      'outside the event pairs is NOT done; kernel times are warm-L2',
             },
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
                          'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
@@ -292,18 +307,115 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def run_batch(args):
+    """
+    C4: a grid of atmospheres (T_eq x log g x metallicity), 50 layers x 20k bins, 3 species, each
+    iterated to convergence (Grid.emission_spectrum's rule, evaluated on the device) and finished
+    with the final emit; atmospheres are sharded over the GPUs with no collective.
+    Metric: converged T-P profiles per second.
+    """
+    import torch
+    import torch.distributed as dist
+    from frei_b200 import synthetic
+    from frei_b200.engine import Engine, FREI_F64, shard_range
+
+    world = int(os.environ.get('WORLD_SIZE', '1'))
+    rank = int(os.environ.get('RANK', '0'))
+    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device('cuda', local_rank)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L, n_lam, S = 50, 20_000, 3
+    n_side = max(1, round(args.batch ** (1 / 3)))
+    B_total = n_side ** 3
+    w = synthetic.make_workload(L, n_lam, S, 2400.0)
+    pl = w['planet']
+    # T_eq 1000..2500 K (sets the initial profile and the irradiation), log g 2.5..4.0 (cgs),
+    # metallicity -1..+2 dex as a multiplier on the mixing ratios (SURVEY 8d)
+    T_ref = np.linspace(1000, 2500, n_side)
+    logg = np.linspace(2.5, 4.0, n_side)
+    met = np.linspace(-1, 2, n_side)
+    tt, gg, mm = [x.ravel() for x in np.meshgrid(T_ref, logg, met, indexing='ij')]
+    lo, hi = shard_range(B_total, rank, world)
+    sel = slice(lo, hi)
+    Bl = hi - lo
+    T0 = tt[sel, None] * (w['P_bar'][None, :] / 0.1) ** 0.1
+    mmr = w['mmr'][None] * (10.0 ** mm[sel])[:, None, None]
+    table = synthetic.device_table(w, FREI_F64, device=dev)
+    eng = Engine(table, w['lam_um'], np.broadcast_to(w['P_bar'], (Bl, L)), T0, mmr, g=10.0 ** gg[sel],
+                 m_bar=pl['m_bar'], alpha=1.0, T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+                 ftoa_scale=(tt[sel] / 2400.0) ** 4)
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up on the real state, then reset
+    for _ in range(max(3, args.warmup)):
+        eng.iteration()
+    eng.reset(T0, mmr)
+    sampler = ClockSampler(local_rank)
+    sync()
+    if rank == 0:
+        sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = eng.launches
+    sync()
+    ev0.record()
+    iters, T = eng.solve_batch(args.max_iterations, check_every=8)
+    ev1.record()
+    sync()
+    ms = ev0.elapsed_time(ev1)
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    it_sum = torch.tensor([float(iters.sum()), float(iters.max()), float((iters >= args.max_iterations).sum())],
+                          dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        agg = [torch.zeros_like(it_sum) for _ in range(world)]
+        dist.all_gather(agg, it_sum)
+        it_sum = torch.stack(agg)
+        tot_it, max_it, capped = float(it_sum[:, 0].sum()), float(it_sum[:, 1].max()), float(it_sum[:, 2].sum())
+    else:
+        tot_it, max_it, capped = [float(x) for x in it_sum]
+    ms = float(t.item())
+    if rank == 0:
+        evals = (2 * tot_it + B_total) * (L - 1) * n_lam          # sweeps actually executed
+        print(json.dumps({
+            'metric': 'converged T-P profiles/s', 'value': B_total / (ms * 1e-3), 'unit': 'profiles/s',
+            'n_gpus': world, 'steps': 1, 'warmup': max(3, args.warmup), 'ms_per_step': ms,
+            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
+            'data': 'synthetic',
+            'config': {'workload': f'C4: batch of {B_total} atmospheres (T_eq x log g x metallicity), '
+                                   '50 layers x 20k lambda bins, 3 species, full RE solve each, '
+                                   'batch-sharded (no collective)',
+                       'mean_iterations': tot_it / B_total, 'max_iterations': max_it,
+                       'hit_iteration_cap': capped, 'iteration_cap': args.max_iterations,
+                       'useful_evals_per_s': evals / (ms * 1e-3)},
+            'gpu_launches': eng.launches - launches0, 'clocks': clocks}))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument('--max-iterations', type=int, default=400)
     ap.add_argument('--gpus', type=int, default=1)
     ap.add_argument('--steps', type=int, default=20)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--table-dtype', type=int, default=64, choices=[32, 64])
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--workload', default='C2', choices=['C1', 'C2', 'C3', 'C4', 'C5'])
+    ap.add_argument('--batch', type=int, default=4096, help='C4: atmospheres in total')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'ours' else args.warmup
     if args.impl == 'reference':
         run_reference(args)
+    elif args.workload == 'C4':
+        run_batch(args)
     else:
         run_ours(args)
 
