@@ -337,9 +337,9 @@ def run_batch(args):
     logg = np.linspace(2.5, 4.0, n_side)
     met = np.linspace(-1, 2, n_side)
     tt, gg, mm = [x.ravel() for x in np.meshgrid(T_ref, logg, met, indexing='ij')]
-    lo, hi = shard_range(B_total, rank, world)
-    sel = slice(lo, hi)
-    Bl = hi - lo
+    # interleaved sharding: neighbouring grid points (similar iteration counts) go to different GPUs
+    sel = slice(rank, B_total, world)
+    Bl = len(range(rank, B_total, world))
     T0 = tt[sel, None] * (w['P_bar'][None, :] / 0.1) ** 0.1
     mmr = w['mmr'][None] * (10.0 ** mm[sel])[:, None, None]
     table = synthetic.device_table(w, FREI_F64, device=dev)
