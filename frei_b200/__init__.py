@@ -12,6 +12,7 @@ from .core import *  # noqa
 from .chemistry import *  # noqa
 from .opacity import *  # noqa
 from .tp import *  # noqa
+from .interp import *  # noqa
 from .twostream import *  # noqa
 
 __version__ = '0.1.0'

@@ -27,6 +27,9 @@ static int set_err(int code, const char* fmt, const char* a = "", const char* b 
     snprintf(g_err, sizeof(g_err), fmt, a, b);
     return code;
 }
+// used by the other translation units of the library
+int frei_set_err(int code, const char* msg) { return set_err(code, "%s%s", msg); }
+
 #define CUDA_TRY(expr)                                                              \
     do {                                                                            \
         cudaError_t e__ = (expr);                                                   \

@@ -9,7 +9,7 @@ import numpy as np
 from . import units as U
 from .chemistry import chemistry
 
-__all__ = ['kappa', 'load_example_opacity', 'OpacityTable']
+__all__ = ['kappa', 'load_example_opacity', 'OpacityTable', 'binned_opacity']
 
 
 class OpacityTable:
@@ -115,3 +115,106 @@ def load_example_opacity(grid, seed=42, scale_factor=20):
     except ImportError:
         tab = OpacityTable(vals, P, T, lam).drop_duplicates('temperature')
     return {"1H2-16O": tab}
+
+
+# ---------------------------------------------------------------------------------------------
+# Load-time path: HELIOS-K / DACE ".bin" directory -> binned tables
+# ---------------------------------------------------------------------------------------------
+def _parse_bin_name(filename):
+    """(wavenumber start, end, temperature, pressure[bar]) from 'Out_<w0>_<w1>_<T>_<p|n><100 log10 P>.bin'
+    (frei/opacity.py:403-410)."""
+    f = filename.split('_')
+    sign = 1 if f[4][0] == 'p' else -1
+    return int(f[1]), int(f[2]), int(f[3]), 10 ** (sign * float(f[4][1:].split('.')[0]) / 100)
+
+
+def read_opacity_dir(opacity_dir):
+    """
+    Read a directory of HELIOS-K float32 ``.bin`` cross-section files into
+    ``(temperature[T], pressure[P], wavelength_um[N] ascending, opacity[T, P, N] float32)`` —
+    what ``opacity_dir_to_netcdf`` (frei/opacity.py:395-483) stores in its netCDF file: first
+    sample dropped, order reversed to ascending wavelength, 0.01 cm^-1 wavenumber grid, and a
+    species with a single pressure duplicated at 1/P.
+    """
+    import os
+    files = [(dp, fn) for dp, _, fns in os.walk(opacity_dir) for fn in sorted(fns) if fn.endswith('.bin')]
+    if not files:
+        raise FileNotFoundError(f'no .bin files under {opacity_dir}')
+    meta = [_parse_bin_name(fn) for _, fn in files]
+    w0, w1 = meta[-1][0], meta[-1][1]
+    wavelength = (1 / np.arange(w0, w1, 0.01) / 1e-4)[1:][::-1]
+    tgrid = np.sort(list({m[2] for m in meta}))
+    pgrid = np.sort(list({m[3] for m in meta}))
+    mirror = len(pgrid) == 1
+    if mirror:
+        pgrid = np.concatenate([pgrid, 10 ** (-1 * np.log10(pgrid))])
+    grid = np.zeros((len(tgrid), len(pgrid), len(wavelength)), dtype='float32')
+    for flip in ([False, True] if mirror else [False]):
+        for (dp, fn), (_, _, T, P) in zip(files, meta):
+            data = np.fromfile(os.path.join(dp, fn), dtype=np.float32)[1:][::-1]
+            if flip:
+                P = 1.0 / P
+            grid[np.argmin(np.abs(tgrid - T)), np.argmin(np.abs(pgrid - P)), :] = data
+    return tgrid.astype(np.float64), pgrid, wavelength, grid
+
+
+def nearest_index(axis, query):
+    """Index of the nearest node, ties to the lower node, clipped at the ends — scipy's
+    ``interp1d(kind='nearest', fill_value='extrapolate')`` as xarray uses it in
+    frei/opacity.py:141-146."""
+    axis = np.asarray(axis, dtype=np.float64)
+    order = np.argsort(axis, kind='stable')
+    mids = 0.5 * (axis[order][1:] + axis[order][:-1])
+    return order[np.searchsorted(mids, np.asarray(query, dtype=np.float64), side='left')]
+
+
+def bin_and_regrid(opacity, wavelength_um, src_T, src_P, temperatures, pressures, wl_bins):
+    """
+    One species of ``binned_opacity`` (groupies=True branch, frei/opacity.py:128-146): crop to the
+    bin range, unit-spacing trapezoid sum per wavelength bin (GPU), times bin width times 1e-3,
+    then nearest-neighbour lookup onto the Grid's (T, P).  Returns an OpacityTable with dims
+    (temperature, pressure, wavelength).
+    """
+    import torch
+    from .interp import groupby_bins_agg, bin_centres
+    wl_bins = U.value(wl_bins, 'um')
+    wl = np.asarray(wavelength_um, dtype=np.float64)
+    keep = (wl > wl_bins.min()) & (wl < wl_bins.max())             # :131-135
+    dev = torch.device('cuda', torch.cuda.current_device())
+    a = torch.from_numpy(np.ascontiguousarray(np.asarray(opacity)[..., keep])).to(dev)
+    binned = groupby_bins_agg(a, wl[keep], wl_bins, func='trapz')  # device tensor [T, P, n_bins]
+    width = torch.from_numpy((wl_bins[1:] - wl_bins[:-1]) * 1e-3).to(dev)     # :139
+    binned = binned * width
+    iT = torch.from_numpy(nearest_index(src_T, U.value(temperatures, 'K'))).to(dev)
+    iP = torch.from_numpy(nearest_index(src_P, U.value(pressures, 'bar'))).to(dev)
+    out = binned.index_select(0, iT).index_select(1, iP).cpu().numpy()
+    tab = OpacityTable(np.transpose(out, (1, 0, 2)), U.value(pressures, 'bar'),
+                       U.value(temperatures, 'K'), bin_centres(wl_bins))
+    tab.dims = ('pressure', 'temperature', 'wavelength')
+    return tab
+
+
+def binned_opacity(temperatures, pressures, wl_bins, lam, groupies=True, species=None, path=None):
+    """
+    Opacity tables of all available species binned to the Grid's wavelengths — signature of
+    frei/opacity.py:66-69.  ``path`` is a glob of HELIOS-K ``.bin`` directories named
+    ``<isotopologue>_*`` (the reference reads the netCDF files it wrote from those directories;
+    netCDF is not available here, the ``.bin`` payload is identical).
+    """
+    import os
+    from glob import glob
+    from .chemistry import iso_to_species
+    if path is None:
+        path = os.path.join(os.path.expanduser('~'), '.frei', '*')
+    dirs = [p for p in sorted(glob(path)) if os.path.isdir(p)]
+    iso = [os.path.basename(p).split('_')[0] for p in dirs]
+    if species is not None:
+        keep = [iso_to_species(i) in species for i in iso]
+        dirs, iso = [d for d, k in zip(dirs, keep) if k], [i for i, k in zip(iso, keep) if k]
+    if not dirs:
+        raise FileNotFoundError(f'no opacity directories match {path}')
+    results = {}
+    for name, d in zip(iso, dirs):
+        T, P, wl, grid = read_opacity_dir(d)
+        results[name] = bin_and_regrid(grid, wl, T, P, temperatures, pressures, wl_bins)
+    return results

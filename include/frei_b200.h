@@ -218,6 +218,18 @@ int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec,
                          const frei_workspace* ws, double* d_T_hist,
                          int32_t prep_first, int32_t prep_next, void* stream);
 
+/* Load-time wavelength binning (frei/interp.py:156-202, 270-307 as called from
+ * frei/opacity.py:137-139): unit-spacing trapezoid sum of consecutive samples that fall in the
+ * same bin, for every leading (temperature, pressure) row.
+ * d_a: [n_rows][row_stride] samples (FREI_F32 | FREI_F64), n_samples <= row_stride;
+ * runs of equal consecutive bin codes [run_start[r], run_end[r]) grouped by bin:
+ * bin b owns runs bin_first_run[b] .. bin_first_run[b+1]-1 (CSR, n_bins + 1 entries);
+ * d_out: [n_rows][n_bins] doubles. */
+int frei_b200_bin_trapz(const void* d_a, int32_t dtype, int64_t n_rows, int64_t n_samples,
+                        int64_t row_stride, const int64_t* d_run_start,
+                        const int64_t* d_run_end, const int32_t* d_bin_first_run,
+                        int32_t n_bins, double* d_out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -557,3 +557,72 @@ def test_batch_solve_device_convergence_matches_per_atmosphere_oracle():
         assert iters[b] == n_it, (b, iters[b], n_it)
         assert np.abs(T[b] - T_ref).max() < 1e-3
         assert _rel(spec[b], s_ref).max() < 1e-6
+
+
+def test_groupby_bins_agg_matches_reference_binning():
+    """Wavelength binning kernel vs the restated numba loop (frei/interp.py:174-202)."""
+    from frei_b200.interp import groupby_bins_agg, cut_codes
+    from oracle import binning_oracle as BO
+    import pandas as pd
+    rs = np.random.RandomState(8)
+    lam_edges = np.concatenate([[0.45], np.logspace(np.log10(0.5), 1, 300)])
+    # cut codes == pandas.cut codes, including values on the edges and outside
+    probe = np.concatenate([lam_edges, np.nextafter(lam_edges, 0), np.nextafter(lam_edges, 100),
+                            rs.uniform(0.3, 12, 500)])
+    assert np.array_equal(cut_codes(probe, lam_edges), np.asarray(pd.cut(probe, lam_edges).codes))
+    for n, dt in ((20000, np.float64), (150000, np.float32), (3100, np.float64)):
+        wl = np.sort(rs.uniform(0.46, 9.99, n))               # inside the outer edges, like the crop
+        a = (10 ** rs.uniform(-3, 2, (3, 4, n))).astype(dt)
+        out = groupby_bins_agg(a, wl, lam_edges, func=np.trapezoid)
+        ref, centres = BO.groupby_bins_agg(a, wl, lam_edges)
+        assert out.shape == (3, 4, 300)
+        np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-300)
+        np.testing.assert_allclose(out.wavelength, centres, rtol=1e-15)
+    # unsorted samples: several runs per bin, and isolated out-of-range samples are skipped
+    wl = rs.uniform(0.46, 9.99, 5000)
+    wl[::97] = 20.0
+    a = rs.uniform(0, 1, (2, 5000))
+    out = groupby_bins_agg(a, wl, lam_edges)
+    ref, _ = BO.groupby_bins_agg(a, wl, lam_edges)
+    np.testing.assert_allclose(out, ref, rtol=1e-12, atol=1e-300)
+    wl[10:12] = 20.0                                          # two consecutive outside -> error
+    with pytest.raises(ValueError, match='negative indices'):
+        groupby_bins_agg(a, wl, lam_edges)
+    with pytest.raises(ValueError, match='negative indices'):
+        BO.groupby_bins_agg(a, wl, lam_edges)
+
+
+def test_binned_opacity_from_bin_directory(tmp_path):
+    """HELIOS-K .bin directory -> binned, regridded tables (frei/opacity.py:66-170, 395-483)."""
+    import frei_b200 as frei
+    from frei_b200.opacity import read_opacity_dir, binned_opacity
+    from oracle import binning_oracle as BO
+    rs = np.random.RandomState(3)
+    d = tmp_path / '1H2-16O__POKAZATEL_e2b'
+    d.mkdir()
+    w0, w1 = 900, 21000                                  # cm^-1  ->  0.476 .. 11.1 micron
+    n = int(round((w1 - w0) / 0.01))
+    raw = {}
+    for T in (500, 1500, 2500):
+        for ptag, P in (('n300', 1e-3), ('p000', 1.0), ('p200', 100.0)):
+            x = (10 ** rs.uniform(-6, 1, n)).astype(np.float32)
+            x.tofile(str(d / f'Out_{w0:05d}_{w1:05d}_{T:05d}_{ptag}.bin'))
+            raw[(T, P)] = x
+    T_ax, P_ax, wl, grid = read_opacity_dir(str(d))
+    assert list(T_ax) == [500, 1500, 2500] and np.allclose(P_ax, [1e-3, 1.0, 100.0])
+    assert grid.shape == (3, 3, n - 1) and np.all(np.diff(wl) > 0)
+    assert np.array_equal(grid[1, 2], raw[(1500, 100.0)][1:][::-1])
+    planet = frei.Planet.from_hot_jupiter()
+    g = frei.Grid(planet, n_wl_bins=150, n_layers=9, T_ref=1800)
+    tabs = binned_opacity(g.init_temperatures, g.pressures, g.wl_bins, g.lam, species=['H2O'],
+                          path=str(tmp_path / '*'))
+    tab = tabs['1H2-16O']
+    ref, centres = BO.binned_opacity_one(grid, wl, T_ax, P_ax, np.asarray(g.init_temperatures),
+                                         np.asarray(g.pressures), np.asarray(g.wl_bins))
+    got = np.transpose(np.asarray(tab.values), (1, 0, 2))         # -> [T, P, wavelength]
+    np.testing.assert_allclose(got, ref, rtol=1e-12, atol=1e-300)
+    np.testing.assert_allclose(tab.wavelength, centres, rtol=1e-14)
+    # the loaded tables feed the hot path
+    g.load_opacities(opacities=tabs)
+    spec, temps, hist, dtaus = g.emission_spectrum(n_timesteps=2)
+    assert np.all(np.isfinite(np.asarray(spec.flux))) and dtaus.shape == (9, 150)
