@@ -30,9 +30,10 @@ __global__ void bin_trapz_kernel(const T* __restrict__ a, int64_t n_samples, int
     double acc = 0.0;
     for (int r = bin_first_run[b]; r < bin_first_run[b + 1]; ++r) {
         const int64_t s = run_start[r], e = run_end[r];
-        // sum_{i=s}^{e-2} (a[i] + a[i+1]) / 2, lanes stride over i
-        for (int64_t i = s + sub; i < e - 1; i += G)
-            acc += ((double)ar[i] + (double)ar[i + 1]) * 0.5;
+        // sum_{i=s}^{e-2} (a[i] + a[i+1]) / 2 = sum_{i=s}^{e-1} a[i] - (a[s] + a[e-1]) / 2:
+        // every sample is read once, lanes stride over i
+        for (int64_t i = s + sub; i < e; i += G) acc += (double)ar[i];
+        if (sub == 0) acc -= 0.5 * ((double)ar[s] + (double)ar[e - 1]);
     }
 #pragma unroll
     for (int o = G / 2; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o, G);
