@@ -11,9 +11,9 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
-#include "../../include/frei_b200.h"
+#include "common.cuh"
 
-extern int frei_set_err(int code, const char* msg);
+
 
 template <typename T, int G>
 __global__ void bin_trapz_kernel(const T* __restrict__ a, int64_t n_samples, int64_t row_stride,

@@ -16,7 +16,7 @@
 #include <string.h>
 #include <math.h>
 
-#include "../../include/frei_b200.h"
+#include "common.cuh"
 
 // ---------------------------------------------------------------------------
 // error plumbing
@@ -40,47 +40,6 @@ int frei_set_err(int code, const char* msg) { return set_err(code, "%s%s", msg);
     do {                                                                            \
         if (!(cond)) return set_err(FREI_E_ARG, "bad argument: %s%s", #cond);       \
     } while (0)
-
-// ---------------------------------------------------------------------------
-// constants (CGS, CODATA 2018 as shipped by astropy >= 4.0)
-// ---------------------------------------------------------------------------
-#define FREI_KB      1.380649e-16
-#define FREI_MP      1.67262192369e-24
-#define FREI_H       6.62607015e-27
-#define FREI_C       2.99792458e10
-#define FREI_SIGSB   5.6703744191844314e-5
-#define FREI_BAR     1e6
-#define FREI_PI      3.141592653589793
-
-#ifndef SWEEP_THREADS
-#define SWEEP_THREADS 128
-#endif
-#ifndef SWEEP_MINB
-#define SWEEP_MINB 4              // resident CTAs per SM the V = 2 sweep kernel is compiled for
-#endif
-#ifndef SWEEP_MINB_V1
-#define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
-#endif
-constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
-constexpr int kWarps = kThreads / 32;
-constexpr int kMaxS = 32;
-constexpr int kPostChunks = 148;        // stage-1 CTAs of the partials reduction (one per SM)
-
-// ---------------------------------------------------------------------------
-// workspace layout
-// ---------------------------------------------------------------------------
-// ws->layer_params holds one record of `rec8` 8-byte words per (atmosphere, level):
-//   [0] dpg = (p1 - p2) / g      [1] invT = 1 / T_i
-//   [2 + 4 s + c]  W[s][c]       mmr-premultiplied weight of corner c of species s
-//   [2 + 4 S + s]  off[s]        int64 element offset of table row (iP, iT) of species s
-// rec8 is even, so records and the W quadruples are 16-byte aligned: the sweep stages the
-// L records of its atmosphere into shared memory with one TMA bulk copy.
-struct LayerParams {
-    double* rec;                // [B][L][rec8]
-    int rec8;
-    int S;
-};
-__host__ __device__ static inline int rec_words(int S) { return (2 + 5 * S + 1) & ~1; }
 
 static inline int64_t layer_params_bytes(int B, int L, int S) {
     return (int64_t)B * L * rec_words(S) * 8;
@@ -409,38 +368,6 @@ __global__ void propagate_kernel(const double* __restrict__ lam, const double* _
 // ---------------------------------------------------------------------------
 // K2+K3: the layer sweep
 // ---------------------------------------------------------------------------
-struct SweepArgs {
-    const void* tab;
-    const double* c1; const double* c2; const double* sigma; const double* w; const double* f_toa;
-    const double* sigma_scale; const double* ftoa_scale;
-    const uint8_t* active;      // [B] or null: atmospheres with 0 are skipped (batch convergence)
-    LayerParams lp;
-    void* F_up; void* F_down; void* dtaus;
-    double* partials;           // [B][rows][L][4], one row per sweep warp
-    int64_t n_lam;
-    int64_t j0, j1;             // wavelength range [j0, j1) covered by this launch
-    int row0, rows;             // first partial row of this launch, total rows of the sweep
-    int B, L, S, N_T;
-};
-
-// Sum four per-lane values across the warp; on return lanes 0, 8, 16, 24 hold the
-// totals of v0, v1, v2, v3 respectively.  Fixed butterfly -> deterministic.
-__device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, double v3, int lane) {
-    const unsigned full = 0xffffffffu;
-    const bool up16 = lane & 16;
-    double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;     // what I send
-    double k0 = up16 ? v2 : v0, k1 = up16 ? v3 : v1;     // what I keep
-    k0 += __shfl_xor_sync(full, s0, 16);
-    k1 += __shfl_xor_sync(full, s1, 16);
-    const bool up8 = lane & 8;
-    double s = up8 ? k0 : k1, k = up8 ? k1 : k0;
-    k += __shfl_xor_sync(full, s, 8);
-    k += __shfl_xor_sync(full, k, 4);
-    k += __shfl_xor_sync(full, k, 2);
-    k += __shfl_xor_sync(full, k, 1);
-    return k;     // lane 0: v0, lane 8: v1, lane 16: v2, lane 24: v3
-}
-
 // V consecutive wavelengths with one (vectorised when V == 2) load/store
 template <int V> struct Vec;
 template <> struct Vec<1> {
@@ -481,24 +408,6 @@ template <> struct Vec<2> {
         *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
     }
 };
-
-// ---- opacity rows: asynchronous staging into shared memory (cp.async) ------------------------
-// Every thread copies the 4 S table elements (x V wavelengths) of the NEXT level into its own
-// slots while it computes the current level, then folds them into k.  The slots of a thread are
-// private to it, so no CTA barrier is involved — only cp.async.wait_group.
-template <int BYTES>
-__device__ __forceinline__ void cp_async(uint32_t dst, const void* src) {
-    if (BYTES == 32) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16;"
-                     ::"r"(dst + 16), "l"((const char*)src + 16) : "memory");
-    } else {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], %2;"
-                     ::"r"(dst), "l"(src), "n"(BYTES == 32 ? 16 : BYTES) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
 // slot of (species s, corner c) for this thread: stage + (4 s + c) * kRowBytes
 template <typename TabT, int S_T, int V>
@@ -571,10 +480,6 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
     }
 #pragma unroll
     for (int v = 0; v < V; ++v) k[v] += sg[v];            // k includes sigma, opacity.py:269
-}
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) {
-    return (uint32_t)__cvta_generic_to_shared(p);
 }
 
 // Per-thread state of the sweep: V wavelengths.
@@ -1160,8 +1065,7 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     ARG_TRY(spec->n_lam == tab->n_lam);
     ARG_TRY(flux && flux->F_up && flux->F_down && ws->partials);
     ARG_TRY(direction == FREI_EMIT || direction == FREI_ABSORB);
-    if (flux->dtype != FREI_F64)
-        return set_err(FREI_E_UNSUPPORTED, "flux dtype %s not supported%s", "f32");
+    ARG_TRY(flux->dtype == FREI_F64 || flux->dtype == FREI_F32);
     ARG_TRY(atm->B <= 65535);
     SweepArgs a;
     a.tab = tab->values;
@@ -1173,6 +1077,10 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
     const SweepPlan plan = make_plan(tab->n_lam, atm->B);
     a.rows = plan.rows;
+    if (flux->dtype == FREI_F32) {               // fp32 arithmetic: sweep_f32.cu, same partials layout
+        a.j0 = 0; a.j1 = tab->n_lam; a.row0 = 0;
+        return frei_launch_sweep_f32(a, tab->dtype, direction, (cudaStream_t)stream);
+    }
     for (int ip = 0; ip < plan.nparts; ++ip) {
         const int V = plan.part[ip].V;
         a.j0 = plan.part[ip].j0; a.j1 = plan.part[ip].j1; a.row0 = plan.part[ip].row0;

@@ -188,12 +188,13 @@ class Engine:
             self.f_toa.copy_(torch.from_numpy(f_toa[self.lo:self.hi]))
 
         # flux state
-        if flux_dtype != FREI_F64:
-            raise NotImplementedError('fp32 flux state is not implemented yet')
+        # FREI_F64: fp64 arithmetic (parity 1e-6 contract); FREI_F32: fp32 state and arithmetic
+        # with fp64 wavelength integrals (1e-4 contract)
         self.flux_dtype = flux_dtype
-        self.F_up = torch.zeros((B, L, n), dtype=f64, device=dev)
-        self.F_down = torch.zeros((B, L, n), dtype=f64, device=dev)
-        self.dtaus = torch.empty((B, L, n), dtype=f64, device=dev) if want_dtaus else None
+        self._fdt = f64 if flux_dtype == FREI_F64 else torch.float32
+        self.F_up = torch.zeros((B, L, n), dtype=self._fdt, device=dev)
+        self.F_down = torch.zeros((B, L, n), dtype=self._fdt, device=dev)
+        self.dtaus = torch.empty((B, L, n), dtype=self._fdt, device=dev) if want_dtaus else None
 
         # workspace
         sizes = [C.c_int64() for _ in range(4)]
@@ -254,7 +255,7 @@ class Engine:
         for dst, src in ((self.F_up, F_up), (self.F_down, F_down)):
             if src is not None:
                 a = np.asarray(src, dtype=np.float64).reshape((self.B, self.L, -1))
-                dst.copy_(torch.from_numpy(np.ascontiguousarray(a[:, :, self.lo:self.hi])))
+                dst.copy_(torch.from_numpy(np.ascontiguousarray(a[:, :, self.lo:self.hi])).to(dst.dtype))
 
     def get_T(self):
         return self.T.cpu().numpy()
@@ -400,7 +401,7 @@ class Engine:
         """
         if with_dtaus and self.dtaus is None:
             torch = _torch()
-            self.dtaus = torch.empty((self.B, self.L, self.n_lam), dtype=torch.float64,
+            self.dtaus = torch.empty((self.B, self.L, self.n_lam), dtype=self._fdt,
                                      device=self.device)
         flux = self._flux_struct(with_dtaus)
         st = self._stream()

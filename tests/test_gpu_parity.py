@@ -626,3 +626,35 @@ def test_binned_opacity_from_bin_directory(tmp_path):
     g.load_opacities(opacities=tabs)
     spec, temps, hist, dtaus = g.emission_spectrum(n_timesteps=2)
     assert np.all(np.isfinite(np.asarray(spec.flux))) and dtaus.shape == (9, 150)
+
+
+@pytest.mark.parametrize('L,n_lam,S', [(50, 5000, 3), (30, 1026, 8), (24, 1333, 2)])
+def test_fp32_mode_sweeps_within_1e4(L, n_lam, S):
+    """
+    fp32 arithmetic mode (flux state + table in fp32, integrals in fp64): per-wavelength fluxes
+    within 1e-4 relative of the fp64 oracle (BASELINE.json north_star) through three RE iterations.
+    Values more than 30 decades below the row maximum are outside fp32's range and compared
+    absolutely.
+    """
+    from frei_b200 import synthetic
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB, FREI_F32
+    w = synthetic.make_workload(L, n_lam, S, table_f32=True)
+    tabs = synthetic.host_tables(w)
+    ref = _oracle_iteration(w, tabs, 3)
+    eng = _engine(w, dtype=FREI_F32, flux_dtype=FREI_F32)
+    k = 0
+    worst = 0.0
+    for it in range(3):
+        for direction in (FREI_EMIT, FREI_ABSORB):
+            eng.sweep(direction, with_dtaus=True)
+            r = ref[k]
+            k += 1
+            for g, x in ((eng.F_up[0], r['Fu']), (eng.F_down[0], r['Fd'])):
+                g = g.cpu().numpy().astype(np.float64)
+                scale = np.maximum(np.abs(x), 1e-30 * np.abs(x).max(axis=1, keepdims=True) + 1e-300)
+                worst = max(worst, float((np.abs(g - x) / scale).max()))
+            assert _rel(eng.dtaus[0].cpu().numpy().astype(np.float64), r['dtaus']).max() < 1e-5
+            lo, hi = (1, L) if direction == FREI_EMIT else (0, L - 1)
+            assert _rel(eng.sums[0].cpu().numpy()[lo:hi], r['bol'][lo:hi]).max() < 1e-5
+            np.testing.assert_allclose(eng.T[0].cpu().numpy(), r['T'], rtol=0, atol=0.05)
+    assert worst < 1e-4, f'fp32 flux error {worst:.3e}'
