@@ -186,14 +186,18 @@ def run_ours(args):
 
     L, n_lam_w, S, T_ref, scaling, wl_text = WORKLOADS[args.workload]
     n_lam_global = n_lam_w * world if scaling == 'weak' else n_lam_w   # weak: bins per GPU fixed
+    if args.flux_dtype == 32:
+        args.table_dtype = 32
     tdtype = FREI_F32 if args.table_dtype == 32 else FREI_F64
+    fdtype = FREI_F32 if args.flux_dtype == 32 else FREI_F64
+    b_flux = 4 if fdtype == FREI_F32 else 8
     w = synthetic.make_workload(L, n_lam_global, S, T_ref, table_f32=(tdtype == FREI_F32))
     lo, hi = shard_range(n_lam_global, rank, world)
     table = synthetic.device_table(w, tdtype, lam_range=(lo, hi), device=dev)
     pl = w['planet']
     eng = Engine(table, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'],
                  m_bar=pl['m_bar'], alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'],
-                 group=group)
+                 group=group, flux_dtype=fdtype, collective=args.collective)
 
     def sync():
         if world > 1:
@@ -234,7 +238,7 @@ def run_ours(args):
 
     # roofline of the dominant kernel (the layer sweep), this rank's launches
     b_tab = 4 if tdtype == FREI_F32 else 8
-    bytes_per_eval = 4 * S * b_tab + 3 * 8
+    bytes_per_eval = 4 * S * b_tab + 3 * b_flux
     sweep_avg_ms = float(np.mean(sweep_ms))
     algo_bytes = (L - 1) * (hi - lo) * bytes_per_eval
     peak, peak_src = read_peaks()
@@ -247,6 +251,7 @@ def run_ours(args):
                         T_star=pl['T_star'], alpha=pl['alpha'])
         grid = Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
         grid.attach_device_table(table, species=w['species'])
+        grid.flux_dtype = fdtype
         k_e2e = max(2, args.steps)
         grid.emission_spectrum(n_timesteps=2, n_zero_crossings=10 ** 9, convergence_dT=0, group=group)
         sync()
@@ -261,7 +266,7 @@ def run_ours(args):
         dt = float(tt.item())
         n_loc = hi - lo
         h2d = (8 * n_lam_global + 8 * L * (2 + S) + 8 * 3) / k_e2e
-        d2h = 3 * L * 8 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e
+        d2h = 3 * L * 8 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e        # results are returned as fp64
         e2e = {'value': (2 * k_e2e + 1) * (L - 1) * n_lam_global / dt, 'unit': UNIT,
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
                'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}) incl. setup, per-iteration '
@@ -278,16 +283,17 @@ def run_ours(args):
         out = {
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
             'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': scaling, 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'scaling': scaling, 'vs_baseline': None, 'dtype': f'f{args.flux_dtype}', 'data': 'synthetic',
             'config': {
                 'workload': wl_text,
                 'n_layers': L, 'n_lambda_global': n_lam_global, 'n_species': S,
-                'table_dtype': f'f{args.table_dtype}', 'flux_dtype': 'f64',
+                'table_dtype': f'f{args.table_dtype}', 'flux_dtype': f'f{args.flux_dtype}',
                 'parallelism': f'lambda-sharded x{world}' if world > 1 else 'single GPU',
+                'collective': ('p2p-fused' if eng._p2p is not None else 'nccl') if world > 1 else None,
                 'l2': 'inputs larger than L2: flux state '
-                      f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB + table '
+                      f'{2 * L * (hi - lo) * b_flux / 1e6:.0f} MB + table '
                       f'{table.values.numel() * b_tab / 1e6:.0f} MB per GPU touched every step'
-                      if 2 * L * (hi - lo) * 8 > 130e6 else
+                      if 2 * L * (hi - lo) * b_flux + table.values.numel() * b_tab > 130e6 else
                       'working set fits L2 (flux state '
                       f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB): 256 MB scratch written between steps '
                       'outside the event pairs is NOT done; kernel times are warm-L2',
@@ -407,7 +413,11 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--table-dtype', type=int, default=64, choices=[32, 64])
+    ap.add_argument('--flux-dtype', type=int, default=64, choices=[32, 64],
+                    help='64: fp64 arithmetic (headline); 32: fp32 state and arithmetic, fp64 integrals')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--collective', default='auto', choices=['auto', 'p2p', 'nccl'],
+                    help='N > 1: fused peer-memory all-reduce inside the post kernel (p2p) or NCCL')
     ap.add_argument('--workload', default='C2', choices=['C1', 'C2', 'C3', 'C4', 'C5'])
     ap.add_argument('--batch', type=int, default=4096, help='C4: atmospheres in total')
     args = ap.parse_args()

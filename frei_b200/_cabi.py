@@ -50,6 +50,11 @@ class frei_flux(C.Structure):
                 ('dtype', c_int32)]
 
 
+class frei_p2p(C.Structure):
+    _fields_ = [('peer_bufs', c_void_p), ('peer_flags', c_void_p), ('error', c_void_p),
+                ('epoch', C.c_uint64), ('rank', c_int32), ('world', c_int32)]
+
+
 class frei_workspace(C.Structure):
     _fields_ = [('layer_params', c_void_p), ('partials', c_void_p), ('sums', c_void_p),
                 ('dT', c_void_p)]
@@ -80,6 +85,8 @@ SIGNATURES = {
                                      c_double, c_void_p, c_void_p]),
     'frei_b200_post': (C.c_int, [P(frei_table), P(frei_atmosphere), P(frei_workspace), c_int64,
                                  c_int32, c_double, c_void_p, c_int32, c_void_p]),
+    'frei_b200_post_p2p': (C.c_int, [P(frei_table), P(frei_atmosphere), P(frei_workspace), c_int64,
+                                     c_int32, c_double, c_void_p, c_int32, P(frei_p2p), c_void_p]),
     'frei_b200_sweep_step': (C.c_int, [P(frei_table), P(frei_spectral), P(frei_atmosphere),
                                        P(frei_flux), c_int32, c_double, P(frei_workspace),
                                        c_void_p, c_int32, c_int32, c_void_p]),

@@ -175,6 +175,7 @@ class Grid(object):
         self.opacities = None
         self._table = None
         self.table_dtype = FREI_F64
+        self.flux_dtype = FREI_F64          # FREI_F32: fp32 arithmetic mode (1e-4 contract)
         self._outputs = _PinnedOutputs()
 
     def __repr__(self):
@@ -237,7 +238,8 @@ class Grid(object):
         return Engine(self.device_table(group), U.value(self.lam, 'um'), P, T0,
                       self._mmr(T0, P, m_bar_g), g=U.gravity_cgs(pl.g), m_bar=m_bar_g,
                       alpha=pl.alpha, T_star=float(U.value(pl.T_star, 'K')),
-                      a_rstar=float(pl.a_rstar), group=group, want_dtaus=want_dtaus)
+                      a_rstar=float(pl.a_rstar), group=group, want_dtaus=want_dtaus,
+                      flux_dtype=self.flux_dtype)
 
     def emission_spectrum(self, n_timesteps=1, n_zero_crossings=2, convergence_dT=3,
                           group=None, dynamic_chemistry=None):
@@ -313,7 +315,7 @@ class Grid(object):
         table = self.device_table(group)
         key = (id(table), id(group), T0.shape, U.value(self.lam, 'um').shape,
                U.gravity_cgs(pl.g), m_bar_g, float(pl.alpha), float(U.value(pl.T_star, 'K')),
-               float(pl.a_rstar), P.tobytes())
+               float(pl.a_rstar), P.tobytes(), self.flux_dtype)
         if getattr(self, '_eng_key', None) != key:
             self._eng = self.make_engine(group=group, want_dtaus=True)
             self._eng_key = key

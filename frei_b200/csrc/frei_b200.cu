@@ -809,6 +809,12 @@ __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const
 struct PostArgs {
     const double* partials; double* chunk_sums; unsigned int* counters; double* sums;
     const uint8_t* active;
+    // fused cross-GPU sum over NVLink peer memory (null peer_bufs = single device)
+    double* const* peer_bufs;            // [world] exchange buffers, doubles [2][world][B][L*4]
+    unsigned long long* const* peer_flags;   // [world] arrival flags [2][world][B]
+    int* p2p_error;
+    unsigned long long epoch;
+    int rank, world, B;
     int rows, rows_per_chunk, nchunks;
     int do_update, do_prep;
 };
@@ -850,7 +856,44 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
     __syncthreads();
     if (!is_last) return;
     __threadfence();
-    const double s2 = cta_column_sum(q.chunk_sums + (int64_t)b * q.nchunks * n, q.nchunks, n, sm_post, G);
+    double s2 = cta_column_sum(q.chunk_sums + (int64_t)b * q.nchunks * n, q.nchunks, n, sm_post, G);
+    if (q.peer_bufs) {
+        // One-shot all-reduce fused into this kernel: every rank stores its [L][4] integrals into
+        // its slot of every peer's exchange buffer (NVLink P2P stores), publishes an arrival flag
+        // with release semantics at system scope, waits for the flags of all ranks in its own
+        // buffer and adds the slots in rank order — the same order on every rank, so all ranks
+        // get bit-identical sums and apply the identical temperature update.  Slots and flags are
+        // double-buffered by the parity of the sweep counter.
+        const int par = (int)(q.epoch & 1ull);
+        const int64_t slot = (((int64_t)par * q.world + q.rank) * q.B + b) * n;
+        if (threadIdx.x < n)
+            for (int r = 0; r < q.world; ++r) q.peer_bufs[r][slot + threadIdx.x] = s2;
+        __threadfence_system();
+        __syncthreads();
+        const int64_t fidx = ((int64_t)par * q.world + q.rank) * q.B + b;
+        if (threadIdx.x < q.world) {
+            unsigned long long* f = q.peer_flags[threadIdx.x] + fidx;
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(q.epoch) : "memory");
+        }
+        if (threadIdx.x < q.world) {
+            const unsigned long long* f = q.peer_flags[q.rank] + ((int64_t)par * q.world + threadIdx.x) * q.B + b;
+            unsigned long long v = 0;
+            int spins = 0;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
+                if (v == q.epoch) break;
+                if (++spins > (1 << 24)) { if (q.p2p_error) *q.p2p_error = 1; break; }   // ~seconds
+                __nanosleep(200);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x < n) {
+            const double* mine = q.peer_bufs[q.rank] + ((int64_t)par * q.world * q.B + b) * n + threadIdx.x;
+            double tot = 0.0;
+            for (int r = 0; r < q.world; ++r) tot += mine[(int64_t)r * q.B * n];
+            s2 = tot;
+        }
+    }
     if (threadIdx.x < n) {
         q.sums[(int64_t)b * n + threadIdx.x] = s2;
         sm_sums[threadIdx.x] = s2;
@@ -1128,7 +1171,8 @@ static void fill_update(UpdateArgs& u, const frei_atmosphere* atm, const frei_wo
 // reduce (+ update T (+ rebuild records)) in one launch
 static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
                        int64_t n_lam, int do_update, int do_prep, int direction,
-                       double alpha_override, double* d_T_hist, cudaStream_t st) {
+                       double alpha_override, double* d_T_hist, cudaStream_t st,
+                       const frei_p2p* p2p = nullptr) {
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
     ARG_TRY(atm->L >= 3 && atm->L <= 256 && atm->B <= 65535);
     PostArgs q;
@@ -1142,6 +1186,15 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     q.counters = reinterpret_cast<unsigned int*>(q.chunk_sums + (int64_t)atm->B * kPostChunks * n);
     q.sums = ws->sums;
     q.active = atm->active;
+    q.peer_bufs = nullptr; q.peer_flags = nullptr; q.p2p_error = nullptr;
+    q.epoch = 0; q.rank = 0; q.world = 1; q.B = atm->B;
+    if (p2p) {
+        ARG_TRY(p2p->peer_bufs && p2p->peer_flags && p2p->world >= 1 && p2p->world <= 64);
+        ARG_TRY(p2p->rank >= 0 && p2p->rank < p2p->world && p2p->epoch > 0);
+        q.peer_bufs = (double* const*)p2p->peer_bufs;
+        q.peer_flags = (unsigned long long* const*)p2p->peer_flags;
+        q.p2p_error = p2p->error; q.epoch = p2p->epoch; q.rank = p2p->rank; q.world = p2p->world;
+    }
     q.do_update = do_update; q.do_prep = do_prep;
     UpdateArgs u{};
     PrepArgs pa{};
@@ -1195,6 +1248,14 @@ int frei_b200_post(const frei_table* tab, const frei_atmosphere* atm, const frei
                    int32_t prep_next, void* stream) {
     return launch_post(tab, atm, ws, n_lam, 1, prep_next ? 1 : 0, direction, alpha_override, d_T_hist,
                        (cudaStream_t)stream);
+}
+
+int frei_b200_post_p2p(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                       int64_t n_lam, int32_t direction, double alpha_override, double* d_T_hist,
+                       int32_t prep_next, const frei_p2p* p2p, void* stream) {
+    ARG_TRY(p2p);
+    return launch_post(tab, atm, ws, n_lam, 1, prep_next ? 1 : 0, direction, alpha_override, d_T_hist,
+                       (cudaStream_t)stream, p2p);
 }
 
 int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec, const frei_atmosphere* atm,

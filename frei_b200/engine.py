@@ -139,7 +139,7 @@ class Engine:
 
     def __init__(self, table, lam_um, pressures_bar, temperatures, mmr, g, m_bar, alpha=1.0,
                  T_star=5800.0, a_rstar=1.0, f_toa=None, ftoa_scale=None, group=None,
-                 flux_dtype=FREI_F64, want_dtaus=False):
+                 flux_dtype=FREI_F64, want_dtaus=False, collective='auto'):
         torch = _torch()
         self.lib = _cabi.load()
         _cabi.require_cuda()
@@ -208,10 +208,44 @@ class Engine:
         self.dT = self.hist[2]
         self._hist_host = None
         self.launches = 0
+        self._p2p = None
+        if group is not None and collective in ('auto', 'p2p'):
+            self._setup_p2p(required=(collective == 'p2p'))
         self._records_stale = True     # level records must be rebuilt before the next sweep
         self._graph = None
         self.sweep_events = None        # list of (start, end) CUDA events around the sweep kernel
         self._build_structs()
+
+    # -- fused cross-GPU sum over peer memory --------------------------------
+    def _setup_p2p(self, required=False):
+        """
+        Exchange buffers in symmetric (peer-mapped) memory for the one-launch
+        reduce + all-reduce + update (``frei_b200_post_p2p``).  Falls back to the NCCL
+        all-reduce between two launches when symmetric memory is unavailable.
+        """
+        torch = _torch()
+        import torch.distributed as dist
+        try:
+            import torch.distributed._symmetric_memory as symm
+            world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+            n = self.B * self.L * 4
+            buf = symm.empty(2 * world * n, dtype=torch.float64, device=self.device)
+            flags = symm.empty(2 * world * self.B, dtype=torch.int64, device=self.device)
+            buf.zero_()
+            flags.zero_()
+            hb = symm.rendezvous(buf, self.group)
+            hf = symm.rendezvous(flags, self.group)
+            torch.cuda.synchronize(self.device)
+            dist.barrier(group=self.group)
+            self._p2p = dict(
+                buf=buf, flags=flags, hb=hb, hf=hf, rank=rank, world=world, epoch=0,
+                bufs=torch.tensor(list(hb.buffer_ptrs), dtype=torch.int64, device=self.device),
+                flgs=torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=self.device),
+                err=torch.zeros(1, dtype=torch.int32, device=self.device))
+        except Exception:
+            if required:
+                raise
+            self._p2p = None
 
     # -- plumbing -----------------------------------------------------------
     def _stream(self):
@@ -432,6 +466,16 @@ class Engine:
             _cabi.check(self.lib.frei_b200_post(C.byref(self._tab), C.byref(self._atm),
                                                 C.byref(self._ws), self.n_lam, direction,
                                                 float(alpha_override), hist_ptr, 1, st))
+            self.launches += 2 + prep_first
+        elif self._p2p is not None:
+            p = self._p2p
+            p['epoch'] += 1
+            arg = _cabi.frei_p2p(p['bufs'].data_ptr(), p['flgs'].data_ptr(), p['err'].data_ptr(),
+                                 p['epoch'], p['rank'], p['world'])
+            _cabi.check(self.lib.frei_b200_post_p2p(C.byref(self._tab), C.byref(self._atm),
+                                                    C.byref(self._ws), self.n_lam, direction,
+                                                    float(alpha_override), hist_ptr, 1,
+                                                    C.byref(arg), st))
             self.launches += 2 + prep_first
         else:
             _cabi.check(self.lib.frei_b200_reduce(C.byref(self._atm), C.byref(self._ws),

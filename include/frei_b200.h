@@ -210,6 +210,27 @@ int frei_b200_post(const frei_table* tab, const frei_atmosphere* atm, const frei
                    int64_t n_lam, int32_t direction, double alpha_override, double* d_T_hist,
                    int32_t prep_next, void* stream);
 
+/* Wavelength-sharded mode without a separate collective: reduce + all-reduce + update_T
+ * (+ layer_prep) in ONE launch.  Every rank stores its [B][L][4] integrals into all peers'
+ * exchange buffers over NVLink peer memory, publishes a system-scope flag, waits for all ranks
+ * and adds the contributions in rank order (bit-identical sums on every rank).
+ * peer_bufs / peer_flags: device arrays of `world` device pointers (peer-mapped, e.g. from
+ * torch.distributed._symmetric_memory) to each rank's doubles [2][world][B][L*4] and
+ * uint64 [2][world][B], both zero-initialised before the first sweep.  epoch = 1, 2, 3, ...
+ * must advance identically on all ranks (one per sweep).  *error (device int, nullable) is set
+ * if a peer does not arrive within a few seconds. */
+typedef struct {
+    void* const* peer_bufs;
+    void* const* peer_flags;
+    int32_t* error;
+    uint64_t epoch;
+    int32_t rank, world;
+} frei_p2p;
+
+int frei_b200_post_p2p(const frei_table* tab, const frei_atmosphere* atm, const frei_workspace* ws,
+                       int64_t n_lam, int32_t direction, double alpha_override, double* d_T_hist,
+                       int32_t prep_next, const frei_p2p* p2p, void* stream);
+
 /* Convenience for one device: [layer_prep if prep_first] + sweep + post, i.e. one
  * emit()/absorb() call of the reference with n_timesteps=1 (frei/core.py:275-299). */
 int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec,

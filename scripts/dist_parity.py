@@ -32,6 +32,8 @@ def solve(group):
     grid = frei.Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
     grid.load_opacities(opacities=op)
     out = grid.emission_spectrum(n_timesteps=40, group=group)
+    global used
+    used = 'p2p-fused' if grid.engine._p2p is not None else ('nccl' if group is not None else 'single')
     return out, grid.n_iterations
 
 
@@ -40,7 +42,7 @@ def solve(group):
 rel = lambda a, b: float(np.max(np.abs(np.asarray(a) - np.asarray(b)) / np.maximum(np.abs(np.asarray(b)), 1e-250)))
 ok = (n1 == n2 and rel(s2.flux, s1.flux) < 1e-9 and np.abs(T2 - T1).max() < 1e-6
       and h1.shape == h2.shape and np.abs(h2 - h1).max() < 1e-6 and rel(d2, d1) < 1e-10)
-print(f'rank {rank}: iterations {n1}/{n2} spectrum rel {rel(s2.flux, s1.flux):.2e} '
+print(f'rank {rank}: [{used}] iterations {n1}/{n2} spectrum rel {rel(s2.flux, s1.flux):.2e} '
       f'T {np.abs(T2 - T1).max():.2e} K dtaus {rel(d2, d1):.2e} -> {"OK" if ok else "MISMATCH"}', flush=True)
 flag = torch.tensor([0 if ok else 1], device='cuda')
 dist.all_reduce(flag)

@@ -13,6 +13,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument('--L', type=int, default=50)
 ap.add_argument('--S', type=int, default=3)
 ap.add_argument('--table-dtype', type=int, default=64)
+ap.add_argument('--flux-dtype', type=int, default=64)
 ap.add_argument('--nlam', type=int, nargs='+', default=[50_000, 100_000, 151_552, 200_000, 303_104, 400_000, 800_000])
 a = ap.parse_args()
 dt = FREI_F32 if a.table_dtype == 32 else FREI_F64
@@ -21,7 +22,8 @@ for n_lam in a.nlam:
     tab = synthetic.device_table(w, dt)
     pl = w['planet']
     eng = Engine(tab, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'], m_bar=pl['m_bar'],
-                 alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'])
+                 alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+                 flux_dtype=FREI_F32 if a.flux_dtype == 32 else FREI_F64)
     for _ in range(3):
         eng.sweep(FREI_EMIT); eng.sweep(FREI_ABSORB)
     eng.sweep_events = []
@@ -36,7 +38,7 @@ for n_lam in a.nlam:
     ms = e0.elapsed_time(e1) / K
     sw = np.mean([x.elapsed_time(y) for x, y in eng.sweep_events])
     ev = (a.L - 1) * n_lam
-    print(f'L {a.L} S {a.S} tab f{a.table_dtype} n_lam {n_lam:8d}: step {ms:.3f} ms  sweep {sw:.4f} ms '
+    print(f'L {a.L} S {a.S} tab f{a.table_dtype} flux f{a.flux_dtype} n_lam {n_lam:8d}: step {ms:.3f} ms  sweep {sw:.4f} ms '
           f'-> kernel {ev / sw / 1e6:.1f} G evals/s, step {2 * ev / ms / 1e6:.1f} G evals/s')
     del eng, tab
     torch.cuda.empty_cache()
