@@ -252,6 +252,7 @@ class Grid(object):
         every sweep (default: only when pyfastchem is installed; the mock's
         ratios do not depend on T).
         """
+        import torch
         if self.opacities is None:
             raise ValueError("Must load opacities before computing emission spectrum.")
         conv_dT = float(U.value(convergence_dT, 'K'))
@@ -293,15 +294,20 @@ class Grid(object):
         spec_local = eng.F_up[0, L - 1]
         dtaus_local = eng.dtaus[0]
         if group is not None:
-            final_temps = eng.T[0].cpu().numpy()
-            spec, dtaus = _gather_lambda(spec_local, dtaus_local, eng, group)
+            from .sharding import gather_lambda
+            both = torch.cat([spec_local[None, :], dtaus_local], dim=0)     # [L + 1][n_local]
+            full = gather_lambda(both, eng.n_lam_global, group, to_numpy=False)
         else:
-            out = self._outputs.get((L + 1, eng.n_lam))        # pinned: [0] spectrum, [1:] dtaus
+            full = None
+        out = self._outputs.get((L + 1, eng.n_lam_global))     # pinned: [0] spectrum, [1:] dtaus
+        if full is not None:
+            out.copy_(full, non_blocking=True)
+        else:
             out[0].copy_(spec_local, non_blocking=True)
             out[1:].copy_(dtaus_local, non_blocking=True)
-            final_temps = eng.T[0].cpu().numpy()               # synchronises the stream
-            arr = self._outputs.hand_out(out)
-            spec, dtaus = arr[0], arr[1:]
+        final_temps = eng.T[0].cpu().numpy()                   # synchronises the stream
+        arr = self._outputs.hand_out(out)
+        spec, dtaus = arr[0], arr[1:]
         self.engine = eng
         return (_make_spectrum(U.wrap(spec, 'flux'), self.lam), U.wrap(final_temps, 'K'),
                 U.wrap(temp_hist, 'K'), dtaus)
@@ -325,13 +331,6 @@ class Grid(object):
 
     def emission_dashboard(self, *args, **kwargs):
         raise NotImplementedError('plotting is outside the scope of frei_b200 (frei/plot.py)')
-
-
-def _gather_lambda(spec_local, dtaus_local, eng, group):
-    """All-gather the wavelength slices of the final spectrum and dtaus."""
-    from .sharding import gather_lambda
-    return (gather_lambda(spec_local, eng.n_lam_global, group),
-            gather_lambda(dtaus_local, eng.n_lam_global, group))
 
 
 # -- T_eff diagnostics (frei/core.py:386-439): cheap host post-processing ----------

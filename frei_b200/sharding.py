@@ -28,10 +28,11 @@ def allreduce_sums(sums, group=None):
     return sums
 
 
-def gather_lambda(local, n_global, group=None):
+def gather_lambda(local, n_global, group=None, to_numpy=True):
     """
     All-gather wavelength slices (last axis, possibly uneven) of ``local`` [..., n_local]
-    into the full [..., n_global] array on every rank (returned as numpy).
+    into the full [..., n_global] array on every rank.  The reassembly happens on the device
+    (one collective, one permute); ``to_numpy=False`` returns the device tensor.
     """
     import torch
     import torch.distributed as dist
@@ -41,7 +42,17 @@ def gather_lambda(local, n_global, group=None):
     lead = tuple(local.shape[:-1])
     buf = torch.zeros(lead + (nmax,), dtype=local.dtype, device=local.device)
     buf[..., :local.shape[-1]] = local
-    out = [torch.empty_like(buf) for _ in range(world)]
-    dist.all_gather(out, buf, group=group)
-    return np.concatenate([o[..., :hi - lo].cpu().numpy() for o, (lo, hi) in zip(out, sizes)],
-                          axis=-1)
+    out = torch.empty((world,) + lead + (nmax,), dtype=local.dtype, device=local.device)
+    if local.device.type == 'cuda':
+        dist.all_gather_into_tensor(out, buf, group=group)
+    else:                                                   # gloo: list form
+        parts = [torch.empty_like(buf) for _ in range(world)]
+        dist.all_gather(parts, buf, group=group)
+        out = torch.stack(parts)
+    nd = out.dim()
+    full = out.permute(*range(1, nd - 1), 0, nd - 1).reshape(lead + (world * nmax,))
+    if any(hi - lo != nmax for lo, hi in sizes):            # drop the padding of short shards
+        keep = torch.cat([torch.arange(r * nmax, r * nmax + hi - lo, device=local.device)
+                          for r, (lo, hi) in enumerate(sizes)])
+        full = full.index_select(full.dim() - 1, keep)
+    return full.cpu().numpy() if to_numpy else full
