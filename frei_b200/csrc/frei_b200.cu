@@ -170,15 +170,24 @@ __global__ void spectral_kernel(const double* __restrict__ lam_um, int64_t n_glo
 // path are finite, positive and far from the denormal range, so plain Newton refinement of the
 // hardware seeds is enough: results are within ~1 ulp (checked by tests through
 // frei_b200_debug_math).
+// Newton steps on the ~2^-20 hardware seeds (measured on B200, scripts/seed_probe.cu:
+// rcp.approx / rsqrt.approx.ftz.f64 are good to 1e-6; one step gives 1e-12, two steps the last
+// bit).  -DFREI_NEWTON_STEPS=1 measured no faster (the sweep is not bound by fp64 issue slots),
+// so the full-precision two-step form is the default.
+#ifndef FREI_NEWTON_STEPS
+#define FREI_NEWTON_STEPS 2
+#endif
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
     y = fma(y, e, y);
+#if FREI_NEWTON_STEPS >= 2
     e = fma(-x, y, 1.0);
-    return fma(y, e, y);
+    y = fma(y, e, y);
+#endif
+    return y;
 }
-
 // sqrt(x) and 1/sqrt(x) for normal positive x
 __device__ __forceinline__ double fast_sqrt(double x, double& rs) {
     double y;
@@ -186,8 +195,10 @@ __device__ __forceinline__ double fast_sqrt(double x, double& rs) {
     const double hx = 0.5 * x;
     double e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
+#if FREI_NEWTON_STEPS >= 2
     e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
+#endif
     rs = y;
     return x * y;                   // ~1.5 ulp; the extra correction step is not worth 3 fp64 slots
 }
