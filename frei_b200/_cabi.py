@@ -107,7 +107,11 @@ def load():
     if _lib is not None:
         return _lib
     path = lib_path()
-    if _build.find_nvcc() is not None:
+    if os.environ.get('FREI_B200_LIB'):          # experiment builds (build.build_variant)
+        path = os.environ['FREI_B200_LIB']
+        if not os.path.exists(path):
+            raise FreiError(f'FREI_B200_LIB={path} does not exist')
+    elif _build.find_nvcc() is not None:
         path = _build.build()
     elif not os.path.exists(path):
         raise FreiError(

@@ -78,5 +78,26 @@ def build(force=False, verbose=False):
     return lib_path()
 
 
+def build_variant(tag, flags):
+    """Experiment builds (A/B of compile-time knobs): ``_lib/variants/libfrei_b200_<tag>.so``,
+    selected at run time with ``FREI_B200_LIB=<path>``.  Not used by the product path."""
+    nvcc = find_nvcc()
+    if nvcc is None:
+        raise RuntimeError('nvcc not found')
+    vdir = os.path.join(LIBDIR, 'variants')
+    os.makedirs(vdir, exist_ok=True)
+    out = os.path.join(vdir, f'libfrei_b200_{tag}.so')
+    cmd = [nvcc] + NVCC_FLAGS + list(flags) + ['-I', INCLUDE, '-o', out] + _sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    with open(out + '.log', 'w') as fh:
+        fh.write(' '.join(cmd) + '\n' + res.stdout + res.stderr)
+    if res.returncode != 0:
+        raise RuntimeError('nvcc failed:\n' + (res.stdout + res.stderr)[-4000:])
+    return out
+
+
 if __name__ == '__main__':
-    print(build(force='--force' in sys.argv, verbose=True))
+    if len(sys.argv) > 2 and sys.argv[1] == '--variant':
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force='--force' in sys.argv, verbose=True))

@@ -35,6 +35,8 @@ constexpr int kPostChunks = 148;        // stage-1 CTAs of the partials reductio
 //   [0] dpg = (p1 - p2) / g      [1] invT = 1 / T_i
 //   [2 + 4 s + c]  W[s][c]       mmr-premultiplied weight of corner c of species s
 //   [2 + 4 S + s]  off[s]        int64 element offset of table row (iP, iT) of species s
+//   [2 + 5 S]      flags         int64, bit 0: every off[s] equals that of level i - 1 (the sweep then
+//                                keeps the table rows it already staged instead of copying them again)
 // rec8 is even, so records and the W quadruples are 16-byte aligned: the sweep stages the
 // L records of its atmosphere into shared memory with one TMA bulk copy.
 struct LayerParams {
@@ -42,7 +44,7 @@ struct LayerParams {
     int rec8;
     int S;
 };
-__host__ __device__ static inline int rec_words(int S) { return (2 + 5 * S + 1) & ~1; }
+__host__ __device__ static inline int rec_words(int S) { return (3 + 5 * S + 1) & ~1; }
 
 // ---------------------------------------------------------------------------
 // K2+K3: arguments of the layer sweep (fp64 and fp32 arithmetic)

@@ -78,6 +78,13 @@ struct PrepArgs {
     int64_t n_lam;
 };
 
+// element offset of the (iP, iT) table row of species s at (vp, vt)
+__device__ __forceinline__ int64_t cell_offset(const PrepArgs& a, int s, double vp, double vt) {
+    const int ip = bracket_index(a.axis_P + (int64_t)s * a.N_P, a.N_P, vp);
+    const int it = a.has_T[s] ? bracket_index(a.axis_T + (int64_t)s * a.N_T, a.N_T, vt) : 0;
+    return (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
+}
+
 __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
     const int L = a.L, S = a.S;
     const double* T = a.T + (int64_t)b * L;
@@ -118,6 +125,15 @@ __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
         if (a.wT) a.wT[li * S + s] = wt;
         if (a.oob) a.oob[li * S + s] = out ? 1 : 0;
     }
+    // same (P, T) cell as level i - 1 for every species?  (T of the neighbour is read, not written,
+    // by this call: callers that update T synchronise before prep_one)
+    int64_t same = 0;
+    if (i > 0) {
+        same = 1;
+        for (int s = 0; s < S; ++s)
+            if (cell_offset(a, s, P[i - 1], T[i - 1]) != reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s]) same = 0;
+    }
+    reinterpret_cast<int64_t*>(rec)[2 + 5 * S] = same;
 }
 
 __global__ void prep_kernel(PrepArgs a) {
@@ -170,37 +186,49 @@ __global__ void spectral_kernel(const double* __restrict__ lam_um, int64_t n_glo
 // path are finite, positive and far from the denormal range, so plain Newton refinement of the
 // hardware seeds is enough: results are within ~1 ulp (checked by tests through
 // frei_b200_debug_math).
-// Newton steps on the ~2^-20 hardware seeds (measured on B200, scripts/seed_probe.cu:
-// rcp.approx / rsqrt.approx.ftz.f64 are good to 1e-6; one step gives 1e-12, two steps the last
-// bit).  -DFREI_NEWTON_STEPS=1 measured no faster (the sweep is not bound by fp64 issue slots),
-// so the full-precision two-step form is the default.
-#ifndef FREI_NEWTON_STEPS
-#define FREI_NEWTON_STEPS 2
+// The hardware seeds (MUFU.RCP64H / RSQ64H) are good to ~1e-6 (measured on B200,
+// scripts/seed_probe.cu).  One third-order step — y0 (1 + e + e^2) for the reciprocal,
+// y0 (1 + e/2 + 3 e^2/8) for the reciprocal square root, e the residual of the seed — leaves a
+// truncation error of e^3 ~ 1e-18, so the result is the correctly rounded value up to ~0.6 ulp with
+// 3 (5) fp64 instructions instead of the 4 (7) of two Newton steps.  -DFREI_SEED_REFINE=2 selects
+// the two-step Newton form, =1 a single Newton step (1e-12, fails the parity tests; timing only).
+#ifndef FREI_SEED_REFINE
+#define FREI_SEED_REFINE 3
 #endif
 __device__ __forceinline__ double fast_rcp(double x) {
     double y;
     asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
     double e = fma(-x, y, 1.0);
+#if FREI_SEED_REFINE == 3
+    return fma(y, fma(e, e, e), y);
+#else
     y = fma(y, e, y);
-#if FREI_NEWTON_STEPS >= 2
+#if FREI_SEED_REFINE == 2
     e = fma(-x, y, 1.0);
     y = fma(y, e, y);
 #endif
     return y;
+#endif
 }
+
 // sqrt(x) and 1/sqrt(x) for normal positive x
 __device__ __forceinline__ double fast_sqrt(double x, double& rs) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+#if FREI_SEED_REFINE == 3
+    const double e = fma(-(x * y), y, 1.0);
+    y = fma(y, fma(0.375, e, 0.5) * e, y);
+#else
     const double hx = 0.5 * x;
     double e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
-#if FREI_NEWTON_STEPS >= 2
+#if FREI_SEED_REFINE == 2
     e = fma(-hx * y, y, 0.5);
     y = fma(y, e, y);
 #endif
+#endif
     rs = y;
-    return x * y;                   // ~1.5 ulp; the extra correction step is not worth 3 fp64 slots
+    return x * y;                   // ~1.5 ulp; a correction step is not worth 3 more fp64 slots
 }
 
 // 2^(j/32), j = 0..31 (correctly rounded); copied to shared memory by the kernels that use it
@@ -469,8 +497,6 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
                                             const double* sg, double* k) {
     const int SS = (S_T > 0) ? S_T : S;
     constexpr int kRowElems = kThreads * V;
-#pragma unroll
-    for (int v = 0; v < V; ++v) k[v] = 0.0;
 #pragma unroll 4
     for (int s = 0; s < SS; ++s) {
         const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
@@ -486,7 +512,7 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
             x = fma(t1[v], wa.y, x);
             x = fma(t2[v], wb.x, x);
             x = fma(t3[v], wb.y, x);
-            k[v] += x;
+            k[v] = (s == 0) ? x : k[v] + x;      // left-to-right sum over species, opacity.py:265-268
         }
     }
 #pragma unroll
@@ -533,11 +559,16 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
     }
 }
 
-// One CTA = kThreads * V consecutive wavelengths of one atmosphere, all layers.  Each thread
-// carries the running stream (F_up for emit, F_down for absorb) and the Planck term of the
-// shared level in registers; the other stream is read stale from HBM one layer ahead of its use
-// and both are written back.  The level records are staged into shared memory by one TMA bulk
-// copy.  The loop body is a single basic block (no data-dependent or uniform branches).
+// A warp-chunk = 32 * V consecutive wavelengths of one atmosphere, all layers.  The grid holds at
+// most one resident wave of CTAs (host: occupancy x SM count) and warp w of CTA c takes the
+// chunks q = w * G + c, + kWarps * G, ... (G = gridDim.x), so the chunks of a partly filled last
+// round are spread evenly over the CTAs — and with them over the SMs — instead of being grabbed
+// in bulk by whichever SMs drain first.  Each thread carries the running stream (F_up for emit,
+// F_down for absorb) and the Planck term of the shared level in registers; the other stream is
+// read stale from HBM one layer ahead of its use and both are written back.  The level records
+// are staged into shared memory by one TMA bulk copy per CTA.  The layer loop body is a single
+// basic block (no data-dependent or uniform branches) and there is no CTA barrier after the
+// staging: warps run their chunks independently.
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
 __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
@@ -547,11 +578,10 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     const int b = blockIdx.y;
     if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
+    const int SS = (S_T > 0) ? S_T : S;
     if (tid < 32) tab[tid] = kExp2Tab[tid];
     double* sm_rec = smem;                       // [L][rec8]
     const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
-    // this warp's wavelength-integral partials: partials[b][cta * kWarps + warp][L][4]
-    double* part = a.partials + ((int64_t)b * a.rows + a.row0 + blockIdx.x * kWarps + warp) * L * 4;
     const uint32_t stage = smem_u32(slot);       // [4 S][kThreads][V] staged table elements
     const int64_t n_lam = a.n_lam;
 
@@ -569,13 +599,32 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
     }
+    const int64_t rowT = (int64_t)a.N_T * n_lam;
+    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
+    const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
+    {   // ---- wait for the records ----
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        }
+    }
 
-    // ---- per-wavelength constants (overlaps the copy) ----
-    const int64_t j_raw = a.j0 + ((int64_t)blockIdx.x * kThreads + tid) * V;
+  const int G = gridDim.x;
+  for (int q = warp * G + blockIdx.x; q < a.rows - a.row0; q += kWarps * G) {
+    // this chunk's wavelength-integral partials: partials[b][row0 + q][L][4]
+    double* part = a.partials + ((int64_t)b * a.rows + a.row0 + q) * L * 4;
+    // ---- per-wavelength constants ----
+    const int64_t j_raw = a.j0 + ((int64_t)q * 32 + lane) * V;
+    if (a.j0 + (int64_t)q * 32 * V >= a.j1) {    // padding row of the partials layout
+        for (int e = lane; e < L * 4; e += 32) part[e] = 0.0;
+        continue;
+    }
     const bool live = j_raw < a.j1;              // (j1 - j0) % V == 0, so all V lanes are in range
     const int64_t j = live ? j_raw : a.j1 - V;
     const TabT* tabj = static_cast<const TabT*>(a.tab) + j;
-    const int64_t rowT = (int64_t)a.N_T * n_lam;
     double* Fu = static_cast<double*>(a.F_up) + (int64_t)b * L * n_lam + j;
     double* Fd = static_cast<double*>(a.F_down) + (int64_t)b * L * n_lam + j;
     double* dt_out = DTAUS ? static_cast<double*>(a.dtaus) + (int64_t)b * L * n_lam + j : nullptr;
@@ -584,7 +633,6 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     Vec<V>::ldg(a.c2 + j, t.c2);
     Vec<V>::ldg(a.sigma + j, t.sg);
     Vec<V>::ldg(a.w + j, t.wj);
-    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
 #pragma unroll
     for (int v = 0; v < V; ++v) { t.sg[v] *= sscale; if (!live) t.wj[v] = 0.0; }
     if (DTAUS && live) {                         // leading row of ones, twostream.py:352/:487
@@ -592,17 +640,6 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
 #pragma unroll
         for (int v = 0; v < V; ++v) one[v] = 1.0;
         Vec<V>::st(dt_out, one);
-    }
-
-    // ---- wait for the records ----
-    {
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
-        }
     }
 
     double F2u[V], F1d[V], dtau[V], red[4], oth[V], nxt[V], k[V];
@@ -622,7 +659,8 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = 1; i < L - 1; ++i) {
-            stage_rows<TabT, S_T, V>(tabj, rec + rec8, S, n_lam, rowT, stage);   // level i + 1
+            if (!(reinterpret_cast<const int64_t*>(rec + rec8)[2 + 5 * SS] & 1))  // level i + 1: new cell
+                stage_rows<TabT, S_T, V>(tabj, rec + rec8, S, n_lam, rowT, stage);
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFd += n_lam;
@@ -642,7 +680,6 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
         }
         {   // top: p_2 extrapolated (in the record), T_2 = T_1, F_2_down = F_TOA, F_2_up discarded
             Vec<V>::ldg(a.f_toa + j, oth);                               // :379-382
-            const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] *= fscale;
             layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, tab, F2u, F1d, dtau, red);
@@ -668,7 +705,8 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = L - 2; i >= 0; --i) {
-            if (i > 0) stage_rows<TabT, S_T, V>(tabj, rec - rec8, S, n_lam, rowT, stage);   // level i - 1
+            if (i > 0 && !(reinterpret_cast<const int64_t*>(rec)[2 + 5 * SS] & 1))   // level i - 1: new cell
+                stage_rows<TabT, S_T, V>(tabj, rec - rec8, S, n_lam, rowT, stage);
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFu -= n_lam;
@@ -692,6 +730,7 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     }
     // rows the sweep does not visit (emit: level 0, absorb: level L-1) contribute nothing
     if (lane < 4) part[((DIR == FREI_EMIT) ? 0 : (L - 1)) * 4 + lane] = 0.0;
+  }
 }
 
 // ---------------------------------------------------------------------------
@@ -919,17 +958,14 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
 // host side of the ABI
 // ---------------------------------------------------------------------------
 // ---- launch plan -------------------------------------------------------------------------------
-// A sweep is one launch of V = 2 CTAs (256 wavelengths each; V = 1 for odd wavelength counts).
-// Every column is a serial recurrence over the layers, so a partly filled last wave of CTAs costs
-// nearly as much as a full one.  -DSWEEP_TAIL_SPLIT hands the wavelengths of such a wave to V = 1
-// CTAs (128 wavelengths, 78 registers) launched right behind the main part; on B200 this measured
-// no faster, so it is off by default.  DESIGN.md 3.1 / 7.
-struct SweepPlan {
-    int nparts;
-    struct { int V; int64_t j0, j1; int row0; unsigned blocks; } part[2];
-    int rows;
-};
-
+// The wavelength axis is cut into warp-chunks of 32 * V wavelengths (V = 2; V = 1 for odd
+// wavelength counts); the partials have one [L][4] row per chunk, padded to whole CTAs (the fp32
+// kernel shares the layout).  For a single atmosphere the grid is capped at one resident wave of
+// CTAs (occupancy x SMs) and the kernel strides over the chunks, which balances a partly filled
+// last round over the SMs: every column is a serial recurrence over the layers, so with the
+// hardware's dynamic CTA placement the SMs that drained first took whole extra CTAs while the
+// others idled (C2: 1.32 waves cost 1.7x one wave).  Batches keep one CTA per kWarps chunks:
+// converged atmospheres exit at once and must not strand the work of the others.
 static int g_num_sms = 0;
 static int num_sms() {
     if (g_num_sms == 0) {
@@ -943,68 +979,62 @@ static int num_sms() {
     return g_num_sms;
 }
 
-static SweepPlan make_plan(int64_t n_lam, int B) {
-    SweepPlan p{};
-    auto add = [&](int V, int64_t j0, int64_t j1) {
-        auto& q = p.part[p.nparts++];
-        q.V = V; q.j0 = j0; q.j1 = j1; q.row0 = p.rows;
-        q.blocks = (unsigned)((j1 - j0 + (int64_t)kThreads * V - 1) / ((int64_t)kThreads * V));
-        p.rows += (int)q.blocks * kWarps;
-    };
-    if (n_lam % 2 != 0) { add(1, 0, n_lam); return p; }
-    const int64_t per_cta = (int64_t)kThreads * 2;
-    const int64_t ctas = (n_lam + per_cta - 1) / per_cta;
-    const int64_t wave = (int64_t)num_sms() * SWEEP_MINB / (B < 1 ? 1 : B);   // CTAs of one wave per atmosphere
-    const int64_t full = wave > 0 ? ctas / wave : 0, rest = wave > 0 ? ctas % wave : 0;
-#ifdef SWEEP_TAIL_SPLIT   // measured on B200: no gain (a column costs ~49 x 1500 cycles of latency at any V)
-    if (wave > 0 && full >= 1 && full < 4 && rest > 0 && rest * 10 < wave * 7) {
-        const int64_t j_split = full * wave * per_cta;
-        add(2, 0, j_split);
-        add(1, j_split, n_lam);
-        return p;
-    }
-#endif
-    add(2, 0, n_lam);
-    return p;
+static inline int sweep_V(int64_t n_lam) { return (n_lam % 2 != 0) ? 1 : 2; }
+static inline int sweep_rows(int64_t n_lam, int /*B*/) {
+    const int64_t per_cta = (int64_t)kThreads * sweep_V(n_lam);
+    return (int)((n_lam + per_cta - 1) / per_cta) * kWarps;
 }
-static inline int sweep_rows(int64_t n_lam, int B) { return make_plan(n_lam, B).rows; }
+
+#ifndef SWEEP_PERSISTENT
+#define SWEEP_PERSISTENT 1        // experiment knob: 0 = one CTA per kWarps chunks for every launch
+#endif
 
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-static int launch_sweep_one(const SweepArgs& a, dim3 grid, size_t smem, cudaStream_t st) {
-    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V, DTAUS>,
-                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    CUDA_TRY(cudaFuncSetAttribute(sweep_kernel<TabT, S_T, DIR, V, DTAUS>,
-                                  cudaFuncAttributePreferredSharedMemoryCarveout,
-                                  (int)cudaSharedmemCarveoutMaxShared));
-    sweep_kernel<TabT, S_T, DIR, V, DTAUS><<<grid, kThreads, smem, st>>>(a);
+static int launch_sweep_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
+    static int resident = -1;     // CTAs per SM of this instantiation (smem differs by < 1 CTA)
+    static size_t smem_set = 0;
+    auto kern = sweep_kernel<TabT, S_T, DIR, V, DTAUS>;
+    if (resident < 0 || smem > smem_set) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      (int)cudaSharedmemCarveoutMaxShared));
+        int nb = 0;
+        CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
+        resident = nb > 0 ? nb : 1;
+        smem_set = smem;
+    }
+    unsigned blocks = (unsigned)((a.rows - a.row0) / kWarps);
+    if (SWEEP_PERSISTENT && a.B == 1) {
+        const unsigned cap = (unsigned)(resident * num_sms());
+        if (blocks > cap) blocks = cap;
+    }
+    kern<<<dim3(blocks, a.B), kThreads, smem, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
 
 template <typename TabT, int S_T, int DIR>
-static int launch_sweep_v(const SweepArgs& a, int V, dim3 grid, size_t smem, cudaStream_t st) {
+static int launch_sweep_v(const SweepArgs& a, int V, size_t smem, cudaStream_t st) {
     if (a.dtaus)
-        return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, grid, smem, st)
-                      : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, grid, smem, st);
-    return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, false>(a, grid, smem, st)
-                  : launch_sweep_one<TabT, S_T, DIR, 1, false>(a, grid, smem, st);
+        return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, smem, st)
+                      : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, smem, st);
+    return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, false>(a, smem, st)
+                  : launch_sweep_one<TabT, S_T, DIR, 1, false>(a, smem, st);
 }
 
 template <typename TabT, int S_T>
-static int launch_sweep_dir(const SweepArgs& a, int direction, int V, dim3 grid, size_t smem,
-                            cudaStream_t st) {
-    if (direction == FREI_EMIT) return launch_sweep_v<TabT, S_T, FREI_EMIT>(a, V, grid, smem, st);
-    return launch_sweep_v<TabT, S_T, FREI_ABSORB>(a, V, grid, smem, st);
+static int launch_sweep_dir(const SweepArgs& a, int direction, int V, size_t smem, cudaStream_t st) {
+    if (direction == FREI_EMIT) return launch_sweep_v<TabT, S_T, FREI_EMIT>(a, V, smem, st);
+    return launch_sweep_v<TabT, S_T, FREI_ABSORB>(a, V, smem, st);
 }
 
 template <typename TabT>
-static int launch_sweep(const SweepArgs& a, int direction, int V, dim3 grid, size_t smem,
-                        cudaStream_t st) {
+static int launch_sweep(const SweepArgs& a, int direction, int V, size_t smem, cudaStream_t st) {
     switch (a.S) {
-        case 1: return launch_sweep_dir<TabT, 1>(a, direction, V, grid, smem, st);
-        case 3: return launch_sweep_dir<TabT, 3>(a, direction, V, grid, smem, st);
-        case 8: return launch_sweep_dir<TabT, 8>(a, direction, V, grid, smem, st);
-        default: return launch_sweep_dir<TabT, 0>(a, direction, V, grid, smem, st);
+        case 1: return launch_sweep_dir<TabT, 1>(a, direction, V, smem, st);
+        case 3: return launch_sweep_dir<TabT, 3>(a, direction, V, smem, st);
+        case 8: return launch_sweep_dir<TabT, 8>(a, direction, V, smem, st);
+        default: return launch_sweep_dir<TabT, 0>(a, direction, V, smem, st);
     }
 }
 
@@ -1129,29 +1159,20 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.F_up = flux->F_up; a.F_down = flux->F_down; a.dtaus = flux->dtaus;
     a.partials = ws->partials;
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
-    const SweepPlan plan = make_plan(tab->n_lam, atm->B);
-    a.rows = plan.rows;
-    if (flux->dtype == FREI_F32) {               // fp32 arithmetic: sweep_f32.cu, same partials layout
-        a.j0 = 0; a.j1 = tab->n_lam; a.row0 = 0;
+    a.rows = sweep_rows(tab->n_lam, atm->B);
+    a.j0 = 0; a.j1 = tab->n_lam; a.row0 = 0;
+    if (flux->dtype == FREI_F32)                 // fp32 arithmetic: sweep_f32.cu, same partials layout
         return frei_launch_sweep_f32(a, tab->dtype, direction, (cudaStream_t)stream);
-    }
-    for (int ip = 0; ip < plan.nparts; ++ip) {
-        const int V = plan.part[ip].V;
-        a.j0 = plan.part[ip].j0; a.j1 = plan.part[ip].j1; a.row0 = plan.part[ip].row0;
-        dim3 grid(plan.part[ip].blocks, atm->B);
+    const int V = sweep_V(tab->n_lam);
 #ifndef SWEEP_SMEM_PAD
 #define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
 #endif
-        const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
-                            (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
-        if (smem > 200 * 1024)
-            return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
-        rc = (tab->dtype == FREI_F32)
-                 ? launch_sweep<float>(a, direction, V, grid, smem, (cudaStream_t)stream)
-                 : launch_sweep<double>(a, direction, V, grid, smem, (cudaStream_t)stream);
-        if (rc) return rc;
-    }
-    return FREI_OK;
+    const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
+                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
+    if (smem > 200 * 1024)
+        return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
+    return (tab->dtype == FREI_F32) ? launch_sweep<float>(a, direction, V, smem, (cudaStream_t)stream)
+                                    : launch_sweep<double>(a, direction, V, smem, (cudaStream_t)stream);
 }
 
 static void fill_prep(PrepArgs& a, const frei_table* tab, const frei_atmosphere* atm,

@@ -256,7 +256,8 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
         cp_async_wait_all();
         gather_f<TabT, V, THREADS>(slot, rec, S, t.sg, k);
         for (int i = 1; i < L - 1; ++i) {
-            stage_rows_f<TabT, V, THREADS>(tabj, rec + rec8, S, n_lam, rowT, stage);
+            if (!(reinterpret_cast<const int64_t*>(rec + rec8)[2 + 5 * S] & 1))    // level i + 1: new cell
+                stage_rows_f<TabT, V, THREADS>(tabj, rec + rec8, S, n_lam, rowT, stage);
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFd += n_lam;
@@ -300,7 +301,8 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
         cp_async_wait_all();
         gather_f<TabT, V, THREADS>(slot, rec, S, t.sg, k);
         for (int i = L - 2; i >= 0; --i) {
-            if (i > 0) stage_rows_f<TabT, V, THREADS>(tabj, rec - rec8, S, n_lam, rowT, stage);
+            if (i > 0 && !(reinterpret_cast<const int64_t*>(rec)[2 + 5 * S] & 1))    // level i - 1: new cell
+                stage_rows_f<TabT, V, THREADS>(tabj, rec - rec8, S, n_lam, rowT, stage);
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];
             pFu -= n_lam;
