@@ -23,6 +23,15 @@
 #ifndef SWEEP_MINB_V1
 #define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
 #endif
+#ifndef SWEEP_FLUX_ASYNC
+#define SWEEP_FLUX_ASYNC 0        // 1: stale stream of the next layer via cp.async slots instead of registers
+#endif
+#ifndef SWEEP_FLUX_LDV
+#define SWEEP_FLUX_LDV 0          // 1: register prefetch of the stale stream through a volatile asm load
+#endif
+#ifndef SWEEP_DEFER_RED
+#define SWEEP_DEFER_RED 0         // 1: warp reduction of a layer's integrals issued one iteration late
+#endif
 constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxS = 32;

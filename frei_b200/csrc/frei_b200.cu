@@ -435,7 +435,11 @@ template <> struct Vec<4> {
 };
 template <> struct Vec<2> {
     static __device__ __forceinline__ void ld(const double* p, double* o) {
+#if SWEEP_FLUX_LDV
+        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p) : "memory");
+#else
         const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
+#endif
     }
     static __device__ __forceinline__ void ldg(const double* p, double* o) {
         const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
@@ -490,6 +494,13 @@ template <> struct SVec<2> {
         const float2 t = *reinterpret_cast<const float2*>(p); o[0] = (double)t.x; o[1] = (double)t.y;
     }
 };
+
+// V doubles from a shared-memory byte address
+template <int V>
+__device__ __forceinline__ void lds_vec(uint32_t addr, double* o) {
+    if (V == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr) : "memory");
+    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[0]) : "r"(addr) : "memory");
+}
 
 // k[v] = sigma + sum_s sum_corners W[s][c] * staged[s][c][v]   (opacity.py:261-269)
 template <typename TabT, int S_T, int V>
@@ -583,6 +594,9 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     double* sm_rec = smem;                       // [L][rec8]
     const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
     const uint32_t stage = smem_u32(slot);       // [4 S][kThreads][V] staged table elements
+    // [2][kThreads][V] doubles behind the table slots: the stale stream of the next layer
+    const uint32_t fstage = smem_u32(reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) +
+                                     (size_t)4 * SS * kThreads * V) + (uint32_t)(tid * V * sizeof(double));
     const int64_t n_lam = a.n_lam;
 
     // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
@@ -642,39 +656,66 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
         Vec<V>::st(dt_out, one);
     }
 
-    double F2u[V], F1d[V], dtau[V], red[4], oth[V], nxt[V], k[V];
+    double F2u[V], F1d[V], dtau[V], red[4], redp[4] = {0.0, 0.0, 0.0, 0.0}, oth[V], nxt[V], k[V];
+    // Two loop-structure options (compile-time, measured on B200 — DESIGN.md 3.1):
+    //  kFluxAsync: the stale stream of the NEXT layer is copied global -> shared with cp.async (two
+    //     thread-private slots used alternately) instead of being prefetched into registers;
+    //  kDeferRed: the warp reduction of a layer's four integrals is issued one iteration late so
+    //     its shuffle chain can overlap the fp64 chain of the next layer; the rows a sweep does not
+    //     visit (emit: level 0, absorb: level L-1) then receive the zeros redp starts with.
+    constexpr bool kFluxAsync = SWEEP_FLUX_ASYNC, kDeferRed = SWEEP_DEFER_RED;
+    uint32_t fcur = fstage, fnxt = fstage + (uint32_t)(kThreads * V * sizeof(double));
+    auto publish = [&](const double* r, int row) {
+        const double r4 = warp_reduce4(r[0], r[1], r[2], r[3], lane);
+        if ((lane & 7) == 0) part[row * 4 + (lane >> 3)] = r4;
+    };
     if (DIR == FREI_EMIT) {
         // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
         const double* rec = sm_rec + rec8;
-        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);
+        const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
+        if (L > 2) {
+            if (kFluxAsync) cp_async<V * 8>(fcur, pFd); else Vec<V>::ld(pFd, nxt);
+        }
+        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
         Vec<V>::ld(Fu + n_lam, t.Fcar);                                  // fluxes_up[1], stale
         const double invT1 = rec[1];
 #pragma unroll
         for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invT1, tab);
-        const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
         double* pFu_out = Fu + 2 * n_lam;                                // fluxes_up[i + 1]
         double* pFd_out = Fd + n_lam;                                    // fluxes_down[i]
         double* pdt = DTAUS ? dt_out + n_lam : nullptr;
-        if (L > 2) Vec<V>::ld(pFd, nxt);
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = 1; i < L - 1; ++i) {
+            if (kFluxAsync) lds_vec<V>(fcur, oth);                       // fluxes_down[i + 1]
+            else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) oth[v] = nxt[v];
+            }
+            pFd += n_lam;
+            if (i + 1 < L - 1) {                                         // one layer ahead
+                if (kFluxAsync) cp_async<V * 8>(fnxt, pFd); else Vec<V>::ld(pFd, nxt);
+            }
             if (!(reinterpret_cast<const int64_t*>(rec + rec8)[2 + 5 * SS] & 1))  // level i + 1: new cell
                 stage_rows<TabT, S_T, V>(tabj, rec + rec8, S, n_lam, rowT, stage);
-#pragma unroll
-            for (int v = 0; v < V; ++v) oth[v] = nxt[v];
-            pFd += n_lam;
-            if (i + 1 < L - 1) Vec<V>::ld(pFd, nxt);                     // one layer ahead
+            else if (kFluxAsync)
+                cp_async_commit();
+            if (kDeferRed) publish(redp, i - 1);
             layer_step<FREI_EMIT, V, false>(t, k, rec[0], oth, rec[rec8 + 1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :392-394
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
             }
-            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
-            if ((lane & 7) == 0) part[i * 4 + (lane >> 3)] = r4;
+            if (kDeferRed) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) redp[c] = red[c];
+            } else {
+                publish(red, i);
+            }
             pFu_out += n_lam; pFd_out += n_lam; rec += rec8;
             if (DTAUS) pdt += n_lam;
+            { const uint32_t x = fcur; fcur = fnxt; fnxt = x; }
             cp_async_wait_all();
             gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         }
@@ -682,54 +723,68 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
             Vec<V>::ldg(a.f_toa + j, oth);                               // :379-382
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] *= fscale;
+            if (kDeferRed) publish(redp, L - 2);
             layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
             }
-            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
-            if ((lane & 7) == 0) part[(L - 1) * 4 + (lane >> 3)] = r4;
+            publish(red, L - 1);
         }
+        if (!kDeferRed && lane < 4) part[lane] = 0.0;                    // level 0 is not visited
     } else {
         const double* rec = sm_rec + (size_t)(L - 2) * rec8;
-        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);
+        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
+        if (kFluxAsync) cp_async<V * 8>(fcur, pFu); else Vec<V>::ld(pFu, nxt);
+        stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
         Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, t.Fcar);               // fluxes_down[L-1]
         const double invTt = rec[rec8 + 1];
 #pragma unroll
         for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invTt, tab);
-        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
         double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                 // fluxes_up[i + 1]
         double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                 // fluxes_down[i]
         double* pdt = DTAUS ? dt_out + n_lam : nullptr;                  // visiting order
-        Vec<V>::ld(pFu, nxt);
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = L - 2; i >= 0; --i) {
+            if (kFluxAsync) lds_vec<V>(fcur, oth);                       // fluxes_up[i], :512
+            else {
+#pragma unroll
+                for (int v = 0; v < V; ++v) oth[v] = nxt[v];
+            }
+            pFu -= n_lam;
+            if (i > 0) {                                                 // one layer ahead
+                if (kFluxAsync) cp_async<V * 8>(fnxt, pFu); else Vec<V>::ld(pFu, nxt);
+            }
             if (i > 0 && !(reinterpret_cast<const int64_t*>(rec)[2 + 5 * SS] & 1))   // level i - 1: new cell
                 stage_rows<TabT, S_T, V>(tabj, rec - rec8, S, n_lam, rowT, stage);
-#pragma unroll
-            for (int v = 0; v < V; ++v) oth[v] = nxt[v];
-            pFu -= n_lam;
-            if (i > 0) Vec<V>::ld(pFu, nxt);                             // one layer ahead, :512
+            else if (kFluxAsync)
+                cp_async_commit();
+            if (kDeferRed) publish(redp, i + 1);
             layer_step<FREI_ABSORB, V, false>(t, k, rec[0], oth, rec[1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :521-522
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
             }
-            const double r4 = warp_reduce4(red[0], red[1], red[2], red[3], lane);
-            if ((lane & 7) == 0) part[i * 4 + (lane >> 3)] = r4;
+            if (kDeferRed) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) redp[c] = red[c];
+            } else {
+                publish(red, i);
+            }
             pFu_out -= n_lam; pFd_out -= n_lam;
             if (DTAUS) pdt += n_lam;
+            { const uint32_t x = fcur; fcur = fnxt; fnxt = x; }
             if (i > 0) {
                 rec -= rec8;
                 cp_async_wait_all();
                 gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
             }
         }
+        if (kDeferRed) publish(redp, 0);
+        else if (lane < 4) part[(L - 1) * 4 + lane] = 0.0;               // level L-1 is not visited
     }
-    // rows the sweep does not visit (emit: level 0, absorb: level L-1) contribute nothing
-    if (lane < 4) part[((DIR == FREI_EMIT) ? 0 : (L - 1)) * 4 + lane] = 0.0;
   }
 }
 
@@ -1168,7 +1223,8 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
 #define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
 #endif
     const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
-                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8);
+                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8) +
+                        (size_t)2 * kThreads * V * sizeof(double);
     if (smem > 200 * 1024)
         return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
     return (tab->dtype == FREI_F32) ? launch_sweep<float>(a, direction, V, smem, (cudaStream_t)stream)
