@@ -47,6 +47,17 @@ WORKLOADS = {
 }
 
 
+def read_traffic(workload, table_dtype, flux_dtype, world):
+    """DRAM bytes per sweep launch from the committed ncu capture of this workload (or None)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            d = json.load(fh)
+        e = d.get(f'{workload}_tab{table_dtype}_flux{flux_dtype}_n{world}')
+        return (e['bytes_per_launch'], e['source']) if e else (None, None)
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
 def read_peaks():
     path = os.path.join(ROOT, 'MEASURED_PEAKS.json')
     try:
@@ -243,6 +254,7 @@ def run_ours(args):
     algo_bytes = (L - 1) * (hi - lo) * bytes_per_eval
     peak, peak_src = read_peaks()
     achieved = algo_bytes / (sweep_avg_ms * 1e-3) / 1e9
+    traffic, traffic_src = read_traffic(args.workload, args.table_dtype, args.flux_dtype, world)
 
     # e2e through the public API: Grid.emission_spectrum with host buffers
     e2e = None
@@ -299,7 +311,14 @@ def run_ours(args):
                       'outside the event pairs is NOT done; kernel times are warm-L2',
             },
             'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': None, 'peak_source': peak_src,
+                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
+                         'traffic_source': traffic_src,
+                         'dram_gbs': (traffic / (sweep_avg_ms * 1e-3) / 1e9) if traffic else None,
+                         'note': 'achieved = algorithmic bytes (SURVEY 8d: 4 S table rows + 3 flux '
+                                 'words per evaluation) / kernel time; table rows shared by the '
+                                 'levels of one (P,T) cell are served on chip, so the DRAM traffic '
+                                 '(traffic, dram_gbs) is lower and frac can exceed 1; the kernel '
+                                 'is bound by fp64 issue + shared-memory bandwidth (DESIGN.md 3.1)',
                          'kernel': 'sweep_kernel', 'kernel_avg_ms': sweep_avg_ms,
                          'bytes_per_eval': bytes_per_eval,
                          'kernel_share_of_step': 2 * sweep_avg_ms / (ms / args.steps)},

@@ -78,32 +78,34 @@ struct PrepArgs {
     int64_t n_lam;
 };
 
-// element offset of the (iP, iT) table row of species s at (vp, vt)
-__device__ __forceinline__ int64_t cell_offset(const PrepArgs& a, int s, double vp, double vt) {
-    const int ip = bracket_index(a.axis_P + (int64_t)s * a.N_P, a.N_P, vp);
-    const int it = a.has_T[s] ? bracket_index(a.axis_T + (int64_t)s * a.N_T, a.N_T, vt) : 0;
-    return (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
-}
-
-__device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
+// Block-cooperative K0 for atmosphere b: the level records of all L levels.
+// The axes are first copied to shared memory (`sm_axes`, S (N_P + N_T) doubles; null = search in
+// global memory): the bracket search is a chain of dependent loads, ~10 L2 round trips per
+// (level, species) when the nodes are read from global memory — it was half of the 26 us of the
+// kernel that follows every sweep.  One thread per (level, species) pair, then one per level
+// for the scalars and the same-cell flag.  Callers that have just written T synchronise first;
+// this function ends with all records written (no trailing barrier).
+__device__ __forceinline__ void prep_block(const PrepArgs& a, int b, double* sm_axes) {
     const int L = a.L, S = a.S;
+    const double* axP = a.axis_P;
+    const double* axT = a.axis_T;
+    if (sm_axes) {
+        for (int e = threadIdx.x; e < S * a.N_P; e += blockDim.x) sm_axes[e] = a.axis_P[e];
+        for (int e = threadIdx.x; e < S * a.N_T; e += blockDim.x) sm_axes[S * a.N_P + e] = a.axis_T[e];
+        axP = sm_axes; axT = sm_axes + S * a.N_P;
+        __syncthreads();
+    }
     const double* T = a.T + (int64_t)b * L;
     const double* P = a.P + (int64_t)b * L;
-    const double g = a.g[b];
-    const double p1 = P[i] * FREI_BAR;
-    double p2;
-    if (i == L - 1) p2 = p1 * (P[L - 2] * FREI_BAR) / (P[L - 3] * FREI_BAR);   // twostream.py:359
-    else p2 = P[i + 1] * FREI_BAR;
-    const int64_t li = (int64_t)b * L + i;
-    double* rec = a.lp.rec + li * a.lp.rec8;
-    rec[0] = (p1 - p2) / g;                                                    // twostream.py:231
-    rec[1] = 1.0 / T[i];
-    for (int s = 0; s < S; ++s) {
-        const double* xp = a.axis_P + (int64_t)s * a.N_P;
-        const double* xt = a.axis_T + (int64_t)s * a.N_T;
+    for (int idx = threadIdx.x; idx < L * S; idx += blockDim.x) {
+        const int i = idx / S, s = idx - i * S;
+        const int64_t li = (int64_t)b * L + i;
+        double* rec = a.lp.rec + li * a.lp.rec8;
+        const double* xp = axP + (int64_t)s * a.N_P;
+        const double* xt = axT + (int64_t)s * a.N_T;
         const double vp = P[i], vt = T[i];
-        int ip = bracket_index(xp, a.N_P, vp);
-        double wp = (vp - xp[ip]) / (xp[ip + 1] - xp[ip]);
+        const int ip = bracket_index(xp, a.N_P, vp);
+        const double wp = (vp - xp[ip]) / (xp[ip + 1] - xp[ip]);
         bool out = (vp < xp[0]) || (vp > xp[a.N_P - 1]);
         int it = 0; double wt = 0.0;
         if (a.has_T[s]) {
@@ -125,21 +127,38 @@ __device__ __forceinline__ void prep_one(const PrepArgs& a, int b, int i) {
         if (a.wT) a.wT[li * S + s] = wt;
         if (a.oob) a.oob[li * S + s] = out ? 1 : 0;
     }
-    // same (P, T) cell as level i - 1 for every species?  (T of the neighbour is read, not written,
-    // by this call: callers that update T synchronise before prep_one)
-    int64_t same = 0;
-    if (i > 0) {
-        same = 1;
-        for (int s = 0; s < S; ++s)
-            if (cell_offset(a, s, P[i - 1], T[i - 1]) != reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s]) same = 0;
+    __syncthreads();                                     // offsets of the neighbouring level
+    const double g = a.g[b];
+    for (int i = threadIdx.x; i < L; i += blockDim.x) {
+        const int64_t li = (int64_t)b * L + i;
+        double* rec = a.lp.rec + li * a.lp.rec8;
+        const double p1 = P[i] * FREI_BAR;
+        double p2;
+        if (i == L - 1) p2 = p1 * (P[L - 2] * FREI_BAR) / (P[L - 3] * FREI_BAR);   // twostream.py:359
+        else p2 = P[i + 1] * FREI_BAR;
+        rec[0] = (p1 - p2) / g;                                                    // twostream.py:231
+        rec[1] = 1.0 / T[i];
+        // same (P, T) cell as level i - 1 for every species?
+        int64_t same = 0;
+        if (i > 0) {
+            same = 1;
+            const int64_t* o1 = reinterpret_cast<const int64_t*>(rec) + 2 + 4 * S;
+            const int64_t* o0 = o1 - a.lp.rec8;
+            for (int s = 0; s < S; ++s) if (o0[s] != o1[s]) same = 0;
+        }
+        reinterpret_cast<int64_t*>(rec)[2 + 5 * S] = same;
     }
-    reinterpret_cast<int64_t*>(rec)[2 + 5 * S] = same;
 }
 
-__global__ void prep_kernel(PrepArgs a) {
-    int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= a.B * a.L) return;
-    prep_one(a, idx / a.L, idx % a.L);
+// bytes of shared memory prep_block wants for the axes (0 = too large, search in global memory)
+static inline size_t prep_axes_bytes(int S, int N_P, int N_T) {
+    const size_t n = (size_t)S * ((size_t)N_P + N_T) * sizeof(double);
+    return n <= 24 * 1024 ? n : 0;
+}
+
+__global__ void prep_kernel(PrepArgs a, int use_smem) {
+    extern __shared__ double sm_prep[];
+    prep_block(a, blockIdx.x, use_smem ? sm_prep : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -849,7 +868,7 @@ __device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int 
 // Block-wide: thread i = level i.  All reads of T precede the barrier, all writes follow it;
 // then (optionally) the records of the new T are rebuilt for the next sweep.
 __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepArgs& pa, int do_prep,
-                                                int b, const double* sums_b) {
+                                                int b, const double* sums_b, double* sm_axes) {
     const int i = threadIdx.x, L = u.L;
     double dT = 0.0, T1 = 0.0;
     if (i < L) {
@@ -896,12 +915,15 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
     }
     if (!do_prep) return;
     __syncthreads();
-    if (i < L) prep_one(pa, b, i);
+    prep_block(pa, b, sm_axes);
 }
 
-__global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums) {
+__global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums,
+                                   int use_smem) {
+    extern __shared__ double sm_upd[];
     if (u.active && !u.active[blockIdx.x]) return;
-    update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4);
+    update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4,
+                    use_smem ? sm_upd : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -922,6 +944,7 @@ struct PostArgs {
     int rank, world, B;
     int rows, rows_per_chunk, nchunks;
     int do_update, do_prep;
+    int axes_smem;                       // the axes of K0 fit behind the sums in shared memory
 };
 
 // Sum `count` rows of n doubles (row stride n) element-wise with all threads of the CTA:
@@ -1006,7 +1029,7 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
     if (threadIdx.x == 0) q.counters[b] = 0u;    // self-cleaning for the next launch
     if (!q.do_update) return;
     __syncthreads();
-    update_and_prep(u, pa, q.do_prep, b, sm_sums);
+    update_and_prep(u, pa, q.do_prep, b, sm_sums, q.axes_smem ? sm_sums + n : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1159,8 +1182,8 @@ int frei_b200_layer_prep(const frei_table* tab, const frei_atmosphere* atm, cons
     a.iP = d_iP; a.iT = d_iT; a.wP = d_wP; a.wT = d_wT; a.oob = d_oob;
     a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_P = tab->N_P; a.N_T = tab->N_T;
     a.n_lam = tab->n_lam;
-    const int n = atm->B * atm->L;
-    prep_kernel<<<(n + 127) / 128, 128, 0, (cudaStream_t)stream>>>(a);
+    const size_t axes = prep_axes_bytes(tab->S, tab->N_P, tab->N_T);
+    prep_kernel<<<atm->B, 128, axes, (cudaStream_t)stream>>>(a, axes > 0);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
@@ -1303,7 +1326,9 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     if (G < 1) return set_err(FREI_E_UNSUPPORTED, "more than 256 levels%s%s");
     if (G > 8) G = 8;
     const int threads = (G * (int)n + 31) / 32 * 32;
-    post_kernel<<<dim3(q.nchunks, atm->B), threads, (size_t)(G + 1) * n * sizeof(double), st>>>(q, u, pa);
+    const size_t axes = do_prep ? prep_axes_bytes(tab->S, tab->N_P, tab->N_T) : 0;
+    q.axes_smem = axes > 0;
+    post_kernel<<<dim3(q.nchunks, atm->B), threads, (size_t)(G + 1) * n * sizeof(double) + axes, st>>>(q, u, pa);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
@@ -1325,8 +1350,13 @@ int frei_b200_update_T(const frei_table* tab, const frei_atmosphere* atm, const 
         if (rc) return rc;
         fill_prep(pa, tab, atm, ws);
     }
-    const int threads = ((atm->L + 31) / 32) * 32;
-    update_prep_kernel<<<atm->B, threads, 0, (cudaStream_t)stream>>>(u, pa, tab ? 1 : 0, ws->sums);
+    int threads = ((atm->L + 31) / 32) * 32;
+    if (tab) {                                   // K0 runs one thread per (level, species)
+        const int want = ((atm->L * tab->S + 31) / 32) * 32;
+        threads = want > 256 ? (threads > 256 ? threads : 256) : (want > threads ? want : threads);
+    }
+    const size_t axes = tab ? prep_axes_bytes(tab->S, tab->N_P, tab->N_T) : 0;
+    update_prep_kernel<<<atm->B, threads, axes, (cudaStream_t)stream>>>(u, pa, tab ? 1 : 0, ws->sums, axes > 0);
     CUDA_TRY(cudaGetLastError());
     return FREI_OK;
 }
