@@ -26,6 +26,9 @@
 #ifndef SWEEP_FLUX_ASYNC
 #define SWEEP_FLUX_ASYNC 0        // 1: stale stream of the next layer via cp.async slots instead of registers
 #endif
+#ifndef SWEEP_E_VOTE
+#define SWEEP_E_VOTE 1            // 1: warp vote selects the E = 1 specialisation of the layer step
+#endif
 #ifndef SWEEP_FLUX_LDV
 #define SWEEP_FLUX_LDV 0          // 1: register prefetch of the stale stream through a volatile asm load
 #endif

@@ -307,29 +307,43 @@ __device__ __forceinline__ double planck(double c1, double c2, double invT, cons
 // The reference's own grouping loses up to ~4e-6 relative accuracy where delta_tau < 1e-6
 // ("conditioning"); this one tracks the exact value of the same formulas.
 // k = total opacity (includes sigma, opacity.py:269), sg = sigma, dpg = (p1 - p2)/g.
-__device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, double F1u, double F2d,
-                                             double B1, double B2, const double* tab, double& F2u,
-                                             double& F1d, double& dtau) {
+// Split in two so that the sweep can vote on omega0 across the warp between the halves:
+// two_stream_front gives delta_tau, omega0 and 1 - omega0; two_stream_tail<E_IS_ONE> the rest.
+// E_IS_ONE = true is the specialisation for omega0 <= 0.1 (E = 1, twostream.py:89-94) in every lane
+// of the warp: it drops the quadratic, its reciprocal and the multiplications by 1 — 9 of the ~90
+// fp64 instructions and one MUFU — and produces bit-identical results to the general form for such
+// lanes (1 * x and x * 1 are exact), so the outcome does not depend on a lane's neighbours.
+__device__ __forceinline__ void two_stream_front(double k, double sg, double dpg, double& dtau,
+                                                 double& w0, double& omw) {
     dtau = dpg * k;                                                     // :371-373
     const double R1 = fast_rcp(sg + k);
-    const double w0 = sg * R1, omw = k * R1;                            // omega0 (:376-378), 1 - omega0
+    w0 = sg * R1; omw = k * R1;                                         // omega0 (:376-378), 1 - omega0
+}
+
+template <bool E_IS_ONE>
+__device__ __forceinline__ void two_stream_tail(double dtau, double w0, double omw, double F1u, double F2d,
+                                                double B1, double B2, const double* tab, double& F2u,
+                                                double& F1d) {
     // Deitrick (2020) Eqn 19 with g_0 = 0 (:89-94), select instead of branch so the whole
     // layer step stays one basic block for the instruction scheduler
-    const bool hi = w0 > 0.1;
-    const double Ep = 1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0);
-    const double Ew = hi ? Ep : 1.0;
-    const double invE = hi ? fast_rcp(Ep) : 1.0;
+    double Ew = 1.0, invE = 1.0;
+    if (!E_IS_ONE) {
+        const bool hi = w0 > 0.1;
+        const double Ep = 1.225 - 0.1777 * w0 - 0.05582 * (w0 * w0);
+        Ew = hi ? Ep : 1.0;
+        invE = hi ? fast_rcp(Ep) : 1.0;
+    }
     const double EmW = Ew - w0;
     double rs;
-    const double a = fast_sqrt(Ew * EmW, rs);
-    const double r = a * invE;                                          // sqrt((E - w0)/E), :143
+    const double a = fast_sqrt(E_IS_ONE ? EmW : Ew * EmW, rs);
+    const double r = E_IS_ONE ? a : a * invE;                           // sqrt((E - w0)/E), :143
     const double u = 2.0 * a * dtau;                                    // T = exp(-u), :139
     double Tr, m, uq;
     bool small;
     exp_neg(u, tab, Tr, m, uq, small);
     const double opr = 1.0 + r;
     const double R2 = fast_rcp(opr * u);
-    const double z = 0.5 * (w0 * invE) * (u * R2);                      // zeta_minus, :145
+    const double z = 0.5 * (E_IS_ONE ? w0 : w0 * invE) * (u * R2);      // zeta_minus, :145
     const double e1 = small ? uq : fma(-(m * opr), R2, 1.0);            // 1 - m/u = (T - 1)/u + 1
     const double zm = z * m, omzm = 1.0 - zm;
     const double chi = -(r + zm) * omzm;                                // :149
@@ -343,6 +357,14 @@ __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, do
     const double pc = (FREI_PI * omw) * R3;                             // pi (1 - w0)/(E - w0)/chi, :152
     F2u = fma(ic, fma(psi, F1u, -xi * F2d), pc * fma(B2, A, H));        // :161-168
     F1d = fma(ic, fma(psi, F2d, -xi * F1u), pc * fma(B1, A, -H));       // :169-176
+}
+
+__device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, double F1u, double F2d,
+                                             double B1, double B2, const double* tab, double& F2u,
+                                             double& F1d, double& dtau) {
+    double w0, omw;
+    two_stream_front(k, sg, dpg, dtau, w0, omw);
+    two_stream_tail<false>(dtau, w0, omw, F1u, F2d, B1, B2, tab, F2u, F1d);
 }
 
 // propagate_fluxes() signature: delta_tau and omega_0 given (twostream.py:97-99).
@@ -556,29 +578,27 @@ struct Lane {
     double Fcar[V], Bcar[V];     // carried stream (F_up for emit, F_down for absorb) and Planck term
 };
 
-// One layer-step for V wavelengths.  `other` = the stale stream entering the layer, `invTn` =
-// 1/T of the level whose Planck term is new this step (ignored when SAME_T: emit's top
-// pseudo-layer has T_2 = T_1, twostream.py:358-363).  Writes the two outgoing streams, the four
-// wavelength-integral contributions of this warp, and optionally delta_tau.
-template <int DIR, int V, bool SAME_T>
-__device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double dpg, const double* other,
+// second half of a layer-step (after the vote on omega0): Planck term of the new level, the
+// two-stream response, the four wavelength-integral contributions
+template <int DIR, int V, bool SAME_T, bool E_IS_ONE>
+__device__ __forceinline__ void layer_tail(Lane<V>& t, const double* w0, const double* omw, const double* other,
                                            double invTn, const double* tab, double* F2u, double* F1d,
-                                           double* dtau, double* red) {
+                                           const double* dtau, double* red) {
     red[0] = red[1] = red[2] = red[3] = 0.0;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn, tab);
         if (DIR == FREI_EMIT) {          // carried = F_1_up, B_1; other = F_2_down; new B = B_2
-            two_stream_k(k[v], t.sg[v], dpg, t.Fcar[v], other[v], t.Bcar[v], Bn, tab,
-                         F2u[v], F1d[v], dtau[v]);
+            two_stream_tail<E_IS_ONE>(dtau[v], w0[v], omw[v], t.Fcar[v], other[v], t.Bcar[v], Bn, tab,
+                                      F2u[v], F1d[v]);
             red[0] = fma(t.wj[v], F2u[v], red[0]);
             red[1] = fma(t.wj[v], other[v], red[1]);
             red[2] = fma(t.wj[v], t.Fcar[v], red[2]);
             red[3] = fma(t.wj[v], F1d[v], red[3]);
             t.Fcar[v] = F2u[v];
         } else {                         // carried = F_2_down, B_2; other = F_1_up; new B = B_1
-            two_stream_k(k[v], t.sg[v], dpg, other[v], t.Fcar[v], Bn, t.Bcar[v], tab,
-                         F2u[v], F1d[v], dtau[v]);
+            two_stream_tail<E_IS_ONE>(dtau[v], w0[v], omw[v], other[v], t.Fcar[v], Bn, t.Bcar[v], tab,
+                                      F2u[v], F1d[v]);
             red[0] = fma(t.wj[v], F2u[v], red[0]);
             red[1] = fma(t.wj[v], t.Fcar[v], red[1]);
             red[2] = fma(t.wj[v], other[v], red[2]);
@@ -587,6 +607,32 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
         }
         t.Bcar[v] = Bn;
     }
+}
+
+// One layer-step for V wavelengths.  `other` = the stale stream entering the layer, `invTn` =
+// 1/T of the level whose Planck term is new this step (ignored when SAME_T: emit's top
+// pseudo-layer has T_2 = T_1, twostream.py:358-363).  Writes the two outgoing streams, the four
+// wavelength-integral contributions of this thread, and delta_tau.  The warp votes on
+// omega0 > 0.1 and takes the E = 1 specialisation when no lane needs the general form.
+template <int DIR, int V, bool SAME_T>
+__device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double dpg, const double* other,
+                                           double invTn, const double* tab, double* F2u, double* F1d,
+                                           double* dtau, double* red) {
+    double w0[V], omw[V];
+    bool hi = false;
+#pragma unroll
+    for (int v = 0; v < V; ++v) {
+        two_stream_front(k[v], t.sg[v], dpg, dtau[v], w0[v], omw[v]);
+        hi = hi || (w0[v] > 0.1);
+    }
+#if SWEEP_E_VOTE
+    if (__any_sync(0xffffffffu, hi))
+        layer_tail<DIR, V, SAME_T, false>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+    else
+        layer_tail<DIR, V, SAME_T, true>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+#else
+    layer_tail<DIR, V, SAME_T, false>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+#endif
 }
 
 // A warp-chunk = 32 * V consecutive wavelengths of one atmosphere, all layers.  The grid holds at
