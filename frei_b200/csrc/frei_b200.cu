@@ -270,7 +270,10 @@ __constant__ double kExp2Tab[32] = {
 __device__ __forceinline__ void exp_neg(double u, const double* tab, double& T, double& m, double& uq,
                                         bool& small) {
     const double MAGIC = 6755399441055744.0;                   // 1.5 * 2^52
-    u = fmin(u, 708.0);
+    // clamp at 708 on the high word (u >= 0: the integer order of the high words is the order of
+    // the doubles; 0x40862000 = high word of 708.0, so u < 708.0003): one integer min instead of
+    // the compare + selects of fmin(); beyond it 2^(n >> 5) underflows to 0 or ~1e-308
+    u = __hiloint2double(min(__double2hiint(u), 0x40862000), __double2loint(u));
     const double tn = fma(u, -46.166241308446828, MAGIC);      // -u * 32 / ln 2
     const int n = __double2loint(tn);                          // rint, <= 0
     const double fn = tn - MAGIC;
@@ -623,7 +626,9 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 #pragma unroll
     for (int v = 0; v < V; ++v) {
         two_stream_front(k[v], t.sg[v], dpg, dtau[v], w0[v], omw[v]);
-        hi = hi || (w0[v] > 0.1);
+        // conservative test on the high word (omega0 >= 0.0999999..., 0x3FB99999 = high word of
+        // 0.1): the general form is correct for every omega0, so a superset only costs time
+        hi = hi || (__double2hiint(w0[v]) >= 0x3FB99999);
     }
 #if SWEEP_E_VOTE
     if (__any_sync(0xffffffffu, hi))

@@ -287,30 +287,24 @@ def test_sweeps_match_oracle(L, n_lam, S, f32):
     assert worst < RTOL_EXACT, f'vs 40-digit evaluation: {worst:.3e}'
 
 
-@pytest.mark.parametrize('L,n_lam,S,T_ref', [(3, 1, 1, 2400.0), (3, 2, 3, 2400.0), (4, 63, 2, 2400.0),
-                                             (7, 65, 3, 2400.0), (5, 257, 8, 2400.0),
-                                             (12, 510, 3, 9000.0), (12, 129, 2, 120.0)])
-def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
+def _one_iteration_with_arbitration(w, align_T):
     """
-    Smallest legal atmosphere (3 levels), wavelength counts around the warp-chunk and CTA sizes
-    (1, 2, 63, 65, 257: odd counts take the one-wavelength-per-thread kernel, the rest the
-    two-per-thread one with a partly filled last chunk), and temperature profiles that leave the
-    opacity table at the hot / cold end, where the interpolation returns 0 (fill_value=0,
-    frei/opacity.py:241-244) for some levels and k falls back to the Rayleigh term alone.
+    emit + absorb on the GPU against the fp64 oracle, the 80-bit oracle and — on the columns where
+    GPU and 80-bit oracle disagree most plus a regular sample — the 40-digit evaluation, which
+    arbitrates where the reference's grouping is too ill-conditioned even for 80 bits
+    (delta_tau down to 1e-12 with omega_0 of order 1).  align_T: start the absorb sweep of the
+    GPU from the oracle's temperatures (its own flux noise enters its temperature update).
     """
     from frei_b200 import synthetic
     from frei_b200.engine import FREI_EMIT, FREI_ABSORB
-    w = synthetic.make_workload(L, n_lam, S, T_ref)
-    if T_ref != 2400.0:
-        inside = (w['T_init'] >= w['axis_T'][0]) & (w['T_init'] <= w['axis_T'][-1])
-        assert 0 < inside.sum() < L            # some levels in the table, some outside
+    L, n_lam = w['L'], w['n_lam']
     tabs = synthetic.host_tables(w)
     ref = _oracle_iteration(w, tabs, 1)
     refx = _oracle_iteration(w, tabs, 1, wd=LD)
     eng = _engine(w)
     gpu_states, worst_x = [], np.zeros(n_lam)
     for k, direction in enumerate((FREI_EMIT, FREI_ABSORB)):
-        if k == 1 and T_ref != 2400.0:
+        if k == 1 and align_T:
             # the fp64 oracle's own flux noise (up to 2e-3 here) enters its temperature update:
             # start the second sweep of both sides from the same temperatures
             eng.set_T(ref[0]['T'])
@@ -328,7 +322,7 @@ def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
         bol = np.asarray(refx[k]['bol'], dtype=np.float64)
         floor = 1e-6 * np.abs(bol).max(axis=1, keepdims=True) + 1e-300
         assert _rel(sums[lo:hi], bol[lo:hi], floor=floor[lo:hi]).max() < 1e-10 + 2 * worst_x.max()
-        if T_ref == 2400.0:
+        if not align_T:
             np.testing.assert_allclose(eng.T[0].cpu().numpy(), ref[k]['T'], rtol=1e-9, atol=1e-6)
     # Levels outside the table have k = sigma (omega_0 = 1/2) and delta_tau down to 1e-7, where even
     # the 80-bit evaluation of the reference's grouping is noisy; the 40-digit value arbitrates on
@@ -349,6 +343,51 @@ def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
             e64 = np.abs(g.astype(LD) - np.asarray(r64, dtype=LD))
             own = np.abs(np.asarray(r64, dtype=LD) - np.asarray(rx, dtype=LD))
             assert bool(((e64 <= 1e-6 * scale) | (e64 <= 2 * own + 1e-8 * scale + 3 * worst_ld * scale)).all())
+
+
+@pytest.mark.parametrize('L,n_lam,S,T_ref', [(3, 1, 1, 2400.0), (3, 2, 3, 2400.0), (4, 63, 2, 2400.0),
+                                             (7, 65, 3, 2400.0), (5, 257, 8, 2400.0),
+                                             (12, 510, 3, 9000.0), (12, 129, 2, 120.0)])
+def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
+    """
+    Smallest legal atmosphere (3 levels), wavelength counts around the warp-chunk and CTA sizes
+    (1, 2, 63, 65, 257: odd counts take the one-wavelength-per-thread kernel, the rest the
+    two-per-thread one with a partly filled last chunk), and temperature profiles that leave the
+    opacity table at the hot / cold end, where the interpolation returns 0 (fill_value=0,
+    frei/opacity.py:241-244) for some levels and k falls back to the Rayleigh term alone.
+    """
+    from frei_b200 import synthetic
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB
+    w = synthetic.make_workload(L, n_lam, S, T_ref)
+    if T_ref != 2400.0:
+        inside = (w['T_init'] >= w['axis_T'][0]) & (w['T_init'] <= w['axis_T'][-1])
+        assert 0 < inside.sum() < L            # some levels in the table, some outside
+    _one_iteration_with_arbitration(w, align_T=(T_ref != 2400.0))
+
+
+def test_scattering_dominated_mixed_warps():
+    """
+    Mixing ratios scaled by 1e-3: Rayleigh scattering competes with absorption, omega_0 crosses
+    0.1 inside the wavelength range, so warps hold lanes on both branches of E(omega_0)
+    (frei/twostream.py:89-94) as well as all-low and all-high warps — the three outcomes of the
+    kernel's warp vote.  One emit + absorb iteration against the fp64 / 80-bit oracles.
+    """
+    from frei_b200 import synthetic
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB
+    L, n_lam, S = 10, 640, 3
+    w = synthetic.make_workload(L, n_lam, S)
+    w['mmr'] = w['mmr'] * 1e-3
+    tabs = synthetic.host_tables(w)
+    pl = w['planet']
+    n_mixed = n_low = n_high = 0
+    for i in range(L):
+        k, sig = O.kappa(tabs, w['T_init'][i], w['P_bar'][i], w['lam_um'], w['mmr'][i], pl['m_bar'])
+        hi = ((sig / (sig + k)) > 0.1).reshape(-1, 64)
+        n_mixed += int((hi.any(axis=1) & ~hi.all(axis=1)).sum())
+        n_low += int((~hi.any(axis=1)).sum())
+        n_high += int(hi.all(axis=1).sum())
+    assert n_mixed > 5 and n_low > 5 and n_high > 5
+    _one_iteration_with_arbitration(w, align_T=True)
 
 def test_reference_kat_and_convergence():
     """
