@@ -268,15 +268,38 @@ class Grid(object):
         L = eng.L
         temp_hists = []
         self.n_iterations = 0
-        for it in range(n_timesteps):
-            if dynamic_chemistry and it > 0:
+        if not dynamic_chemistry and n_timesteps > 0:
+            # Static mixing ratios: the convergence rule of frei/core.py:301-318 runs on the device
+            # (Engine.enable_batch_convergence, the tracker of the batch mode with B = 1): once
+            # it fires, every later kernel of this atmosphere exits at once, so iterations can be
+            # queued back to back and the host looks at the flag only every `check_every`
+            # iterations instead of synchronising after each one.  The temperature history is
+            # written by the update kernel into a device buffer, one [2][L] slot per iteration.
+            check_every = 4
+            eng.enable_batch_convergence(n_zero_crossings, conv_dT)
+            blocks, it, stopped = [], 0, False
+            while it < n_timesteps and not stopped:
+                nb = min(256, n_timesteps - it)
+                hist = torch.zeros((nb, 2, 1, L), dtype=torch.float64, device=eng.device)
+                blocks.append(hist)
+                for j in range(nb):
+                    eng.sweep(FREI_EMIT, T_hist=hist[j, 0])
+                    eng.sweep(FREI_ABSORB, T_hist=hist[j, 1])
+                    it += 1
+                    if it % check_every == 0 and not bool(eng.active.any().item()):
+                        stopped = True
+                        break
+            still = bool(eng.active.any().item())
+            self.n_iterations = it if still else int(eng.iterations_done[0].item())
+            eng.disable_batch_convergence()
+            h = torch.cat(blocks, dim=0)[:self.n_iterations, :, 0, :].cpu().numpy()   # [n][2][L]
+            temp_hists = [h[k].T for k in range(self.n_iterations)]
+        for it in range(n_timesteps if dynamic_chemistry else 0):
+            if it > 0:
                 eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
-            if dynamic_chemistry:
-                eng.sweep(FREI_EMIT, T_hist=eng.hist[0])
-                eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
-                eng.sweep(FREI_ABSORB, T_hist=eng.hist[1])
-            else:
-                eng.iteration()
+            eng.sweep(FREI_EMIT, T_hist=eng.hist[0])
+            eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
+            eng.sweep(FREI_ABSORB, T_hist=eng.hist[1])
             T_emit, T_absorb, dT = eng.read_history()
             temp_hists.append(np.stack([T_emit[0], T_absorb[0]], axis=1))
             dT = dT[0]

@@ -57,15 +57,27 @@ class Slice:
         return out[6]
 
 
+def _single_threaded_blas():
+    """np.dot (the sharded trapezoid sums) would otherwise start one BLAS thread per core in
+    every worker process; with N workers that oversubscribes the host N-fold (measured: 20x slower)."""
+    try:
+        from threadpoolctl import threadpool_limits
+        return threadpool_limits(limits=1)
+    except Exception:                # pragma: no cover
+        import contextlib
+        return contextlib.nullcontext()
+
+
 def _worker(conn, wl_args, lo, hi, lam_stride):
-    sl = Slice(wl_args, lo, hi, lam_stride)
-    conn.send('ready')
-    while True:
-        msg = conn.recv()
-        if msg is None:
-            break
-        direction, T = msg
-        conn.send(sl.sweep(direction, T))
+    with _single_threaded_blas():
+        sl = Slice(wl_args, lo, hi, lam_stride)
+        conn.send('ready')
+        while True:
+            msg = conn.recv()
+            if msg is None:
+                break
+            direction, T = msg
+            conn.send(sl.sweep(direction, T))
 
 
 class ParallelOracle:
@@ -101,7 +113,8 @@ class ParallelOracle:
 
     def _sweep(self, direction):
         if self.local is not None:
-            bol = self.local.sweep(direction, self.T)
+            with _single_threaded_blas():        # "cores: 1" means one thread
+                bol = self.local.sweep(direction, self.T)
         else:
             for c in self.conns:
                 c.send((direction, self.T))
