@@ -1,7 +1,8 @@
 #!/bin/bash
-# time for exactly one wave of sweep CTAs at 1..4 CTAs/SM (128 threads, 256 wavelengths each)
-for cfg in "210000 37888" "100000 75776" "60000 113664" "0 151552"; do
-  set -- $cfg
-  echo "== smem pad $1 B, n_lam $2"
-  FREI_B200_NVCC_EXTRA="-DSWEEP_SMEM_PAD=$1" python scripts/size_scan.py --nlam $2 2>&1 | tail -1
+# Sweep-kernel throughput vs resident CTAs per SM: extra dynamic shared memory (SWEEP_SMEM_PAD) caps
+# the occupancy, the persistent grid follows it.  Builds the variants in place (nvcc is in the image),
+# so run it where a GPU is: scripts/occ_scan.sh
+for pad in 150000 80000 40000 0; do
+  python frei_b200/build.py --variant occ$pad -DSWEEP_MINB=4 -DSWEEP_SMEM_PAD=$pad > /dev/null
 done
+scripts/ab_libs.sh "--nlam 200000 800000" occ150000 occ80000 occ40000 occ0
