@@ -269,11 +269,15 @@ def run_ours(args):
         grid.attach_device_table(table, species=w['species'])
         grid.flux_dtype = fdtype
         k_e2e = max(2, args.steps)
-        grid.emission_spectrum(n_timesteps=2, n_zero_crossings=10 ** 9, convergence_dT=0, group=group)
+        # N > 1: every rank keeps its own wavelength slice of the results (gather='local'), so the
+        # job's outputs cross N PCIe links in parallel; gather='all' would copy the N-times larger
+        # weak-scaled result to the host of every rank
+        grid.emission_spectrum(n_timesteps=2, n_zero_crossings=10 ** 9, convergence_dT=0, group=group,
+                               gather='local')
         sync()
         t0 = time.perf_counter()
         grid.emission_spectrum(n_timesteps=k_e2e, n_zero_crossings=10 ** 9, convergence_dT=0,
-                               group=group)
+                               group=group, gather='local')
         sync()
         dt = time.perf_counter() - t0
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
@@ -285,9 +289,11 @@ def run_ours(args):
         d2h = 2 * L * 8 + 0.25 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e  # T history, flag polls, fp64 results
         e2e = {'value': (2 * k_e2e + 1) * (L - 1) * n_lam_global / dt, 'unit': UNIT,
                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}) incl. setup, device-side '
-                       'convergence rule polled every 4 iterations, final emit, T history + '
-                       'spectrum + dtaus D2H into pinned host arrays',
+               'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}'
+                       + (", group=WORLD, gather='local'" if world > 1 else '') +
+                       ') incl. setup, device-side convergence rule polled every 4 iterations, '
+                       'final emit, T history + spectrum + dtaus D2H into pinned host arrays'
+                       + (' (each rank: its own wavelength slice)' if world > 1 else ''),
                'seconds': dt}
     except Exception as exc:                                   # pragma: no cover
         e2e = {'value': None, 'error': repr(exc)}

@@ -90,6 +90,10 @@ SIGNATURES = {
     'frei_b200_sweep_step': (C.c_int, [P(frei_table), P(frei_spectral), P(frei_atmosphere),
                                        P(frei_flux), c_int32, c_double, P(frei_workspace),
                                        c_void_p, c_int32, c_int32, c_void_p]),
+    'frei_b200_diagnostics_scratch_bytes': (c_int64, [c_int64]),
+    'frei_b200_diagnostics': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
+                                        c_void_p]),
     'frei_b200_bin_trapz': (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_void_p, c_int32, c_void_p, c_void_p]),
 }

@@ -14,7 +14,7 @@ from .chemistry import chemistry
 from .engine import Engine, DeviceTable, FREI_EMIT, FREI_ABSORB, FREI_F64, shard_range
 from .tp import pressure_grid, temperature_grid
 
-__all__ = ['Grid', 'Planet', 'effective_temperature', 'Spectrum']
+__all__ = ['Grid', 'Planet', 'effective_temperature', 'contribution_function', 'Spectrum']
 
 
 def wavelength_grid(min_micron=0.5, max_micron=10, n_bins=500, lam=None):
@@ -242,12 +242,17 @@ class Grid(object):
                       flux_dtype=self.flux_dtype)
 
     def emission_spectrum(self, n_timesteps=1, n_zero_crossings=2, convergence_dT=3,
-                          group=None, dynamic_chemistry=None):
+                          group=None, dynamic_chemistry=None, gather='all'):
         """
         Iterate emit/absorb sweeps towards radiative equilibrium and return
         ``(spectrum, final_temps, temperature_history, dtaus)`` exactly as
         frei/core.py:233-338.  ``group`` shards the wavelength axis over a
-        torch.distributed process group (every rank returns the full result).
+        torch.distributed process group.  ``gather='all'`` (default): every rank
+        returns the full result, as a single-process call of the reference would;
+        ``gather='local'``: every rank returns only its own wavelength slice
+        ``self.lam_range`` of the spectrum and of ``dtaus`` (the temperatures are
+        replicated anyway) — the results of an N-GPU job then leave the GPUs over
+        N PCIe links in parallel instead of N times over each of them.
         ``dynamic_chemistry``: recompute mixing ratios from the current T before
         every sweep (default: only when pyfastchem is installed; the mock's
         ratios do not depend on T).
@@ -255,6 +260,8 @@ class Grid(object):
         import torch
         if self.opacities is None:
             raise ValueError("Must load opacities before computing emission spectrum.")
+        if gather not in ('all', 'local'):
+            raise ValueError("gather must be 'all' or 'local'")
         conv_dT = float(U.value(convergence_dT, 'K'))
         if dynamic_chemistry is None:
             try:
@@ -316,13 +323,19 @@ class Grid(object):
         eng.sweep(FREI_EMIT, alpha_override=1.0, with_dtaus=True)
         spec_local = eng.F_up[0, L - 1]
         dtaus_local = eng.dtaus[0]
-        if group is not None:
+        lam_out = self.lam
+        self.lam_range = (0, eng.n_lam_global)
+        if group is not None and gather == 'all':
             from .sharding import gather_lambda
             both = torch.cat([spec_local[None, :], dtaus_local], dim=0)     # [L + 1][n_local]
             full = gather_lambda(both, eng.n_lam_global, group, to_numpy=False)
         else:
             full = None
-        out = self._outputs.get((L + 1, eng.n_lam_global))     # pinned: [0] spectrum, [1:] dtaus
+            if group is not None:                              # this rank's slice only
+                self.lam_range = (eng.lo, eng.hi)
+                lam_out = U.wrap(U.value(self.lam, 'um')[self.lam_range[0]:self.lam_range[1]], 'um')
+        n_out = self.lam_range[1] - self.lam_range[0]
+        out = self._outputs.get((L + 1, n_out))                # pinned: [0] spectrum, [1:] dtaus
         if full is not None:
             out.copy_(full, non_blocking=True)
         else:
@@ -332,7 +345,7 @@ class Grid(object):
         arr = self._outputs.hand_out(out)
         spec, dtaus = arr[0], arr[1:]
         self.engine = eng
-        return (_make_spectrum(U.wrap(spec, 'flux'), self.lam), U.wrap(final_temps, 'K'),
+        return (_make_spectrum(U.wrap(spec, 'flux'), lam_out), U.wrap(final_temps, 'K'),
                 U.wrap(temp_hist, 'K'), dtaus)
 
     def _solver_engine(self, group):
@@ -352,22 +365,114 @@ class Grid(object):
             self._eng.reset(T0, self._mmr(T0, P, m_bar_g))
         return self._eng
 
+    def diagnostics(self, contribution_function=False, pressure_milne=False, group=None):
+        """
+        T_eff (frei/core.py:386-439) and optionally the contribution function
+        (frei/plot.py:63-79) of the last ``emission_spectrum`` solve, computed from the
+        spectrum and ``dtaus`` still resident in HBM — no host copies of the large arrays.
+        With a wavelength-sharded ``group`` the three sums are added over the ranks and the
+        per-wavelength outputs cover this rank's slice ``self.lam_range``.
+        Returns a dict with ``T_eff``, ``T_milne``, ``T_planck`` [K] and, on request,
+        ``pressure_milne`` [n_lambda] and ``contribution_function`` [n_layers][n_lambda]
+        (numpy arrays).
+        """
+        eng = getattr(self, 'engine', None)
+        if eng is None or eng.dtaus is None:
+            raise ValueError("Must run emission_spectrum before computing its diagnostics.")
+        L = eng.L
+        sums, pm, cf = _device_diagnostics(
+            eng.lam_dev[eng.lo:eng.hi], eng.w, eng.P[0], eng.T[0], eng.F_up[0, L - 1], eng.dtaus[0],
+            want_pressure=pressure_milne, want_cf=contribution_function)
+        if group is not None:
+            import torch.distributed as dist
+            dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+        P, T = eng.P[0].cpu().numpy(), eng.T[0].cpu().numpy()
+        t_milne, t_planck = _teff_from_sums(sums.cpu().numpy(), P, T)
+        out = {'T_eff': U.wrap(np.mean([t_milne, t_planck]), 'K'), 'T_milne': U.wrap(t_milne, 'K'),
+               'T_planck': U.wrap(t_planck, 'K')}
+        if pm is not None:
+            out['pressure_milne'] = pm.cpu().numpy()
+        if cf is not None:
+            out['contribution_function'] = cf.cpu().numpy()
+        return out
+
     def emission_dashboard(self, *args, **kwargs):
         raise NotImplementedError('plotting is outside the scope of frei_b200 (frei/plot.py)')
 
 
-# -- T_eff diagnostics (frei/core.py:386-439): cheap host post-processing ----------
+# -- T_eff diagnostics (frei/core.py:386-439) and contribution function (frei/plot.py:63-79) ------
+# on the device (frei_b200_diagnostics): the reference loops over the wavelengths in Python, one
+# np.interp call each — about a second for 200k bins; here the spectrum and dtaus of a solve
+# stay in HBM and three sums come back.
+def _trapz_weights_cm(lam_um):
+    lam_cm = np.asarray(lam_um, dtype=np.float64) * 1e-4
+    w = np.zeros_like(lam_cm)
+    if lam_cm.shape[0] > 1:
+        w[1:-1] = 0.5 * (lam_cm[2:] - lam_cm[:-2])
+        w[0] = 0.5 * (lam_cm[1] - lam_cm[0])
+        w[-1] = 0.5 * (lam_cm[-1] - lam_cm[-2])
+    return w
+
+
+def _device_diagnostics(lam_um, w_cm, P_bar, T, spec, dtaus, want_pressure=False, want_cf=False):
+    """
+    Run ``frei_b200_diagnostics`` on arrays that are numpy (uploaded) or torch device tensors
+    (used in place).  Returns ``(sums[3] device tensor, pressure_milne or None, cf or None)``.
+    """
+    import torch
+    lib = _cabi.load()
+    _cabi.require_cuda()
+    dev = None
+    for x in (dtaus, spec, lam_um):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            dev = x.device
+    if dev is None:
+        dev = torch.device('cuda', torch.cuda.current_device())
+
+    def dbl(x):
+        if not isinstance(x, torch.Tensor):
+            x = torch.from_numpy(np.ascontiguousarray(np.asarray(x, dtype=np.float64)))
+        return x.to(device=dev, dtype=torch.float64).contiguous()
+
+    d_dtaus, d_spec, d_lam, d_w, d_P, d_T = (dbl(x) for x in (dtaus, spec, lam_um, w_cm, P_bar, T))
+    L, n = d_dtaus.shape
+    if d_spec.shape != (n,) or d_lam.shape != (n,) or d_w.shape != (n,) or d_P.shape != (L,) or d_T.shape != (L,):
+        raise ValueError('inconsistent shapes: dtaus [L][n_lam], spectrum/lam [n_lam], pressures/temperatures [L]')
+    scratch = torch.empty(max(1, lib.frei_b200_diagnostics_scratch_bytes(n) // 8), dtype=torch.float64, device=dev)
+    sums = torch.empty(3, dtype=torch.float64, device=dev)
+    pm = torch.empty(n, dtype=torch.float64, device=dev) if want_pressure else None
+    cf = torch.empty((L, n), dtype=torch.float64, device=dev) if want_cf else None
+    with torch.cuda.device(dev):
+        _cabi.check(lib.frei_b200_diagnostics(
+            d_dtaus.data_ptr(), d_spec.data_ptr(), d_lam.data_ptr(), d_w.data_ptr(), d_P.data_ptr(),
+            d_T.data_ptr(), L, n, _cabi.ptr(pm), _cabi.ptr(cf), scratch.data_ptr(), sums.data_ptr(),
+            torch.cuda.current_stream(dev).cuda_stream))
+    return sums, pm, cf
+
+
+def _teff_from_sums(sums, P_bar, T):
+    """(T_milne, T_planck) from the three device sums (frei/core.py:397-403, 413-414)."""
+    s = [float(x) for x in sums]
+    p_avg = s[0] / s[1]
+    P_bar, T = np.asarray(P_bar, dtype=np.float64), np.asarray(T, dtype=np.float64)
+    return float(np.interp(p_avg, P_bar[::-1], T[::-1])), float((s[2] / U.sigma_sb) ** (1 / 4))
+
+
+def _grid_arrays(grid, spec, final_temps):
+    lam_um = U.value(grid.lam, 'um')
+    lo, hi = getattr(grid, 'lam_range', None) or (0, lam_um.shape[0])
+    flux = U.value(spec.flux, 'flux')
+    w = _trapz_weights_cm(lam_um)
+    if flux.shape[0] != lam_um.shape[0]:          # a rank's slice (gather='local')
+        lam_um, w = lam_um[lo:hi], w[lo:hi]
+    return lam_um, w, U.value(grid.pressures, 'bar'), U.value(final_temps, 'K'), flux
+
+
 def effective_temperature_milne(grid, spec, dtaus, final_temps):
     """Photosphere temperature from Milne's tau ~ 2/3 (frei/core.py:386-405)."""
-    lam_um = U.value(grid.lam, 'um')
-    P = U.value(grid.pressures, 'bar')
-    T = U.value(final_temps, 'K')
-    flux = U.value(spec.flux, 'flux')
-    pressure_milne = np.ones_like(lam_um)
-    for i in range(dtaus.shape[1]):
-        pressure_milne[i] = np.interp(2 / 3, np.exp(-dtaus[:, i]), P)
-    p_avg = np.average(pressure_milne, weights=flux * (lam_um * 1e-4))
-    return U.wrap(np.interp(p_avg, P[::-1], T[::-1]), 'K')
+    lam_um, w, P, T, flux = _grid_arrays(grid, spec, final_temps)
+    sums, _, _ = _device_diagnostics(lam_um, w, P, T, flux, dtaus)
+    return U.wrap(_teff_from_sums(sums.cpu().numpy(), P, T)[0], 'K')
 
 
 def effective_temperature_planck(grid, spec):
@@ -380,6 +485,21 @@ def effective_temperature_planck(grid, spec):
 
 def effective_temperature(grid, spec, dtaus, final_temps):
     """Mean of the Milne and Stefan-Boltzmann estimates (frei/core.py:417-439)."""
-    a = float(U.value(effective_temperature_milne(grid, spec, dtaus, final_temps), 'K'))
-    b = float(U.value(effective_temperature_planck(grid, spec), 'K'))
+    lam_um, w, P, T, flux = _grid_arrays(grid, spec, final_temps)
+    sums, _, _ = _device_diagnostics(lam_um, w, P, T, flux, dtaus)
+    a, b = _teff_from_sums(sums.cpu().numpy(), P, T)
     return U.wrap(np.mean([a, b]), 'K')
+
+
+def contribution_function(grid, dtaus, final_temps):
+    """
+    Normalised contribution function [n_layers][n_lambda] in level order, as the dashboard
+    shows it (``cf[::-1]`` of frei/plot.py:63-83).
+    """
+    lam_um = U.value(grid.lam, 'um')
+    P, T = U.value(grid.pressures, 'bar'), U.value(final_temps, 'K')
+    n = np.asarray(dtaus).shape[1]
+    lo, hi = (0, n) if n == lam_um.shape[0] else grid.lam_range
+    zeros = np.zeros(n)
+    _, _, cf = _device_diagnostics(lam_um[lo:hi], zeros, P, T, zeros, dtaus, want_cf=True)
+    return cf.cpu().numpy()

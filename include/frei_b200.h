@@ -251,6 +251,27 @@ int frei_b200_bin_trapz(const void* d_a, int32_t dtype, int64_t n_rows, int64_t 
                         const int64_t* d_run_end, const int32_t* d_bin_first_run,
                         int32_t n_bins, double* d_out, void* stream);
 
+/* Device-side post-processing of a finished solve, one thread per wavelength of
+ * this device's slice; nothing but three sums has to leave the GPU for T_eff.
+ *   d_dtaus [L][n_lam], d_spec [n_lam] (fluxes_up of the top level) as returned by the final
+ *   emit; d_lam_um / d_w: this slice of the wavelength grid [micron] and of the global
+ *   trapezoid weights [cm] (frei_b200_spectral_setup); d_P_bar, d_T [L].
+ * Outputs:
+ *   d_pressure_milne [n_lam] or NULL: np.interp(2/3, np.exp(-dtaus[:, j]), pressures) with
+ *     numpy's own search path (the sequence is not sorted in general), frei/core.py:392-395;
+ *   d_cf [L][n_lam] or NULL: contribution function normalised per wavelength, level order
+ *     (the reference's cf[::-1]), frei/plot.py:63-79, 83;
+ *   d_sums[3] = { sum_j p_milne_j F_j lam_j,  sum_j F_j lam_j,  sum_j w_j F_j }: numerator and
+ *     denominator of the flux-weighted mean pressure (frei/core.py:397-401) and
+ *     np.trapz(spec.flux, lam) (frei/core.py:413); with a sharded wavelength axis the caller adds
+ *     the three numbers over the ranks.
+ * d_scratch: frei_b200_diagnostics_scratch_bytes(n_lam) bytes.  Fixed summation order. */
+int64_t frei_b200_diagnostics_scratch_bytes(int64_t n_lam);
+int frei_b200_diagnostics(const double* d_dtaus, const double* d_spec, const double* d_lam_um,
+                          const double* d_w, const double* d_P_bar, const double* d_T, int32_t L,
+                          int64_t n_lam, double* d_pressure_milne, double* d_cf, double* d_scratch,
+                          double* d_sums, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

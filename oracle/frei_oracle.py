@@ -41,7 +41,7 @@ __all__ = [
     'hot_jupiter', 'rayleigh_sigma', 'bracket', 'bilinear_weights',
     'kappa', 'kappa_explicit', 'E', 'propagate_fluxes', 'bolometric_flux',
     'layer_thermo', 'emit', 'absorb', 'emission_spectrum',
-    'effective_temperature', 'load_example_opacity', 'iso_to_mass',
+    'effective_temperature', 'pressure_milne', 'contribution_function', 'load_example_opacity', 'iso_to_mass',
     'mock_mmr', 'trapz_weights', 'thermo_from_bol',
 ]
 
@@ -556,14 +556,38 @@ def emission_spectrum(tables, init_temperatures, pressures_bar, lam_um, planet, 
 # ---------------------------------------------------------------------------
 # T_eff diagnostics  (frei/core.py:386-439) — used by the reference's KAT
 # ---------------------------------------------------------------------------
+def pressure_milne(pressures_bar, dtaus):
+    """Per-wavelength tau ~ 2/3 pressure: the loop of frei/core.py:390-395 (np.interp itself)."""
+    out = np.ones(dtaus.shape[1])
+    for i in range(dtaus.shape[1]):
+        out[i] = np.interp(2 / 3, np.exp(-dtaus[:, i]), pressures_bar)
+    return out
+
+
 def effective_temperature_milne(pressures_bar, lam_um, spec, dtaus, final_temps):
     """frei/core.py:386-405."""
     lam_cm = lam_um * 1e-4
-    pressure_milne = np.ones_like(lam_um)
-    for i in range(dtaus.shape[1]):
-        pressure_milne[i] = np.interp(2 / 3, np.exp(-dtaus[:, i]), pressures_bar)
-    return np.interp(np.average(pressure_milne, weights=spec * lam_cm),
+    return np.interp(np.average(pressure_milne(pressures_bar, dtaus), weights=spec * lam_cm),
                      pressures_bar[::-1], final_temps[::-1])
+
+
+def contribution_function(lam_um, pressures_bar, temps, dtaus):
+    """
+    Normalised contribution function of the dashboard, frei/plot.py:63-79, returned as the
+    reference plots it (``cf[::-1]``, level order, frei/plot.py:83).  Parity unpinned by the
+    reference: the expression sits inside a matplotlib routine with no test or fixture.
+    """
+    dtaus = np.asarray(dtaus)
+    tau = np.cumsum(dtaus[::-1], axis=0)                                   # :63
+    nus = 1.0 / (lam_um * 1e-4)                                            # :64, lam -> cm^-1
+    hcperk = h * c / k_B                                                   # :65
+    dlogP = (np.log10(pressures_bar.max()) - np.log10(pressures_bar.min())) / (len(pressures_bar) - 1)
+    k = 10 ** -dlogP                                                       # :70
+    dParr = (1 - k) * pressures_bar                                        # :71
+    cf = (np.exp(-tau) * dtaus[::-1] * (pressures_bar[::-1, None] / dParr[::-1, None]) *
+          nus ** 3 / np.expm1(hcperk * nus / temps[::-1, None]))           # :73-77
+    cf /= np.sum(cf, axis=0)                                               # :79
+    return cf[::-1]
 
 
 def effective_temperature_planck(lam_um, spec):

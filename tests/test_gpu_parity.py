@@ -760,3 +760,61 @@ def test_fp32_mode_sweeps_within_1e4(L, n_lam, S):
             assert _rel(eng.sums[0].cpu().numpy()[lo:hi], r['bol'][lo:hi]).max() < 1e-5
             np.testing.assert_allclose(eng.T[0].cpu().numpy(), r['T'], rtol=0, atol=0.05)
     assert worst < 1e-4, f'fp32 flux error {worst:.3e}'
+
+
+# ---------------------------------------------------------------------------
+# device-side post-processing: T_eff sums, Milne pressure, contribution function
+# ---------------------------------------------------------------------------
+@pytest.mark.parametrize('L,n_lam', [(2, 7), (3, 33), (4, 300), (5, 257), (9, 1000), (30, 5000), (100, 777)])
+def test_diagnostics_kernel_matches_numpy_interp_on_unsorted_columns(L, n_lam):
+    """
+    frei/core.py:392-395 calls np.interp on exp(-dtaus[:, j]), which is not sorted in general
+    (row 0 is the row of ones); the kernel restates numpy's search path.  Random unsorted
+    columns exercise the linear (len <= 4), guess and bisection branches.
+    """
+    import torch
+    from frei_b200.core import _device_diagnostics, _trapz_weights_cm
+    rng = np.random.default_rng(100 + L)
+    dtaus = 10.0 ** rng.uniform(-6, 1.5, (L, n_lam))
+    dtaus[0] = 1.0
+    kind = rng.integers(0, 3, n_lam)
+    mono = np.sort(dtaus[1:], axis=0)[::-1]                 # decreasing upwards, like a real solve
+    dtaus[1:, kind == 1] = mono[:, kind == 1]
+    dtaus[1:, kind == 2] = mono[:, kind == 2] * rng.uniform(0.5, 2.0, (L - 1, int((kind == 2).sum())))
+    lam = np.logspace(np.log10(0.5), 1, n_lam)
+    P = np.logspace(-6, np.log10(200), L)[::-1].copy()
+    T = 2400.0 * (P / 0.1) ** 0.1
+    spec = 10.0 ** rng.uniform(8, 13, n_lam)
+    w = _trapz_weights_cm(lam)
+    sums, pm, cf = _device_diagnostics(lam, w, P, T, spec, dtaus, want_pressure=True, want_cf=True)
+    torch.cuda.synchronize()
+    pm_ref = O.pressure_milne(P, dtaus)
+    np.testing.assert_allclose(pm.cpu().numpy(), pm_ref, rtol=1e-12, atol=0)
+    sums = sums.cpu().numpy()
+    wt = spec * lam * 1e-4
+    np.testing.assert_allclose(sums, [(pm_ref * wt).sum(), wt.sum(), (w * spec).sum()], rtol=1e-12)
+    cf_ref = O.contribution_function(lam, P, T, dtaus)
+    cf = cf.cpu().numpy()
+    assert np.abs(cf.sum(axis=0) - 1).max() < 1e-12
+    np.testing.assert_allclose(cf, cf_ref, rtol=1e-10, atol=1e-300)
+
+
+def test_grid_diagnostics_from_resident_state():
+    """Grid.diagnostics(): T_eff and contribution function of a solve without host copies."""
+    import frei_b200 as frei
+    planet = frei.Planet.from_hot_jupiter()
+    grid = frei.Grid(planet=planet, T_ref=2400)
+    grid.load_opacities(opacities=frei.load_example_opacity(grid, scale_factor=1))
+    spec, temps, hist, dtaus = grid.emission_spectrum(n_timesteps=3)
+    d = grid.diagnostics(contribution_function=True, pressure_milne=True)
+    P, lam = np.asarray(grid.pressures), np.asarray(grid.lam)
+    flux, temps = np.asarray(spec.flux), np.asarray(temps)
+    assert abs(d['T_milne'] - O.effective_temperature_milne(P, lam, flux, dtaus, temps)) < 1e-6
+    assert abs(d['T_planck'] - O.effective_temperature_planck(lam, flux)) < 1e-6
+    assert abs(d['T_eff'] - O.effective_temperature(P, lam, flux, dtaus, temps)) < 1e-6
+    assert abs(d['T_eff'] - frei.effective_temperature(grid, spec, dtaus, temps)) < 1e-9
+    np.testing.assert_allclose(d['pressure_milne'], O.pressure_milne(P, dtaus), rtol=1e-12)
+    np.testing.assert_allclose(d['contribution_function'], O.contribution_function(lam, P, temps, dtaus),
+                               rtol=1e-10, atol=1e-300)
+    np.testing.assert_allclose(frei.contribution_function(grid, dtaus, temps), d['contribution_function'],
+                               rtol=1e-13, atol=1e-300)

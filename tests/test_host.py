@@ -114,3 +114,26 @@ def test_shard_ranges_partition_the_axis():
         assert all(a[1] == b[0] for a, b in zip(r, r[1:]))
         assert max(hi - lo for lo, hi in r) - min(hi - lo for lo, hi in r) <= 1
         assert r[1] == shard_range(n, 1, w)
+
+
+def test_trapezoid_weights_reproduce_np_trapz():
+    from frei_b200.core import _trapz_weights_cm
+    rs = np.random.RandomState(3)
+    for n in (1, 2, 3, 500):
+        lam = np.sort(rs.uniform(0.5, 10, n))
+        F = rs.uniform(1, 2, n)
+        trapz = getattr(np, 'trapezoid', None) or np.trapz
+        np.testing.assert_allclose((_trapz_weights_cm(lam) * F).sum(), trapz(F, lam * 1e-4), rtol=1e-14, atol=0)
+
+
+def test_emission_spectrum_argument_errors():
+    """Same error behaviour as frei/core.py:259-260; the gather mode is validated before any GPU work."""
+    import pytest
+    grid = frei.Grid(frei.Planet.from_hot_jupiter())
+    with pytest.raises(ValueError, match='Must load opacities'):
+        grid.emission_spectrum()
+    grid.opacities = {'1H2-16O': None}
+    with pytest.raises(ValueError, match='gather'):
+        grid.emission_spectrum(gather='rank0')
+    with pytest.raises(ValueError, match='emission_spectrum'):
+        grid.diagnostics()

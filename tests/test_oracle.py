@@ -265,3 +265,28 @@ def test_reference_run_case_D_mock_chemistry(ref_run):
     for i, name in enumerate(['1H2-16O', '12C-16O', '48Ti-16O']):
         np.testing.assert_allclose(d['vmr'][name], 1.5e-3, rtol=1e-14)
         np.testing.assert_allclose(d['mmr'][name], ref[i], rtol=1e-14)
+
+
+def test_diagnostics_restatements(default_case):
+    """pressure_milne / contribution_function (frei/core.py:390-395, frei/plot.py:63-79): the
+    Milne pressure is what effective_temperature_milne averages, the contribution function is
+    normalised per wavelength and invariant under the wavelength-only and layer-constant factors."""
+    rs = np.random.RandomState(7)
+    L, n = 30, 64
+    P = O.pressure_grid(L, np.log10(1e-6), np.log10(200))
+    T = O.temperature_grid(P, 2400.0, 0.1, 0.1)
+    lam = np.logspace(np.log10(0.5), 1, n)
+    dtaus = np.vstack([np.ones(n), np.sort(10.0 ** rs.uniform(-6, 1, (L - 1, n)), axis=0)[::-1]])
+    spec = rs.uniform(1e10, 1e13, n)
+    pm = O.pressure_milne(P, dtaus)
+    assert pm.shape == (n,) and np.all((pm >= P.min()) & (pm <= P.max()))
+    t_m = np.interp(np.average(pm, weights=spec * lam * 1e-4), P[::-1], T[::-1])
+    assert t_m == O.effective_temperature_milne(P, lam, spec, dtaus, T)
+    cf = O.contribution_function(lam, P, T, dtaus)
+    assert cf.shape == (L, n) and np.all(cf >= 0)
+    np.testing.assert_allclose(cf.sum(axis=0), 1.0, rtol=1e-13)
+    # level order: the top level (index L-1) has tau = its own dtau
+    top = np.exp(-dtaus[-1]) * dtaus[-1] / np.expm1(O.h * O.c / O.k_B / (lam * 1e-4) / T[-1])
+    bot_tau = dtaus.sum(axis=0)
+    bot = np.exp(-bot_tau) * dtaus[0] / np.expm1(O.h * O.c / O.k_B / (lam * 1e-4) / T[0])
+    np.testing.assert_allclose(cf[-1] / cf[0], top / bot, rtol=1e-9)
