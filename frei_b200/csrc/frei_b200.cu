@@ -115,25 +115,42 @@ struct PrepArgs {
     int64_t n_lam;
 };
 
+// Where a block finds the per-level inputs of atmosphere b.  Either views of global memory or a
+// staged copy in shared memory (post_kernel copies them before it waits for the sweep, see there).
+struct LevelView {
+    const double* T;        // [L]
+    const double* P;        // [L]
+    const double* mmr;      // [L][S]
+    int64_t* off;           // [L][S] shared-memory scratch for the row offsets, or null
+};
+__device__ __forceinline__ LevelView global_levels(const double* T, const double* P, const double* mmr,
+                                                   int b, int L, int S) {
+    LevelView v;
+    v.T = T + (int64_t)b * L; v.P = P + (int64_t)b * L; v.mmr = mmr ? mmr + (int64_t)b * L * S : nullptr;
+    v.off = nullptr;
+    return v;
+}
+
+// Copy the axes of K0 into shared memory (S (N_P + N_T) doubles); the caller synchronises.
+__device__ __forceinline__ void stage_axes(const double* axis_P, const double* axis_T, int S, int N_P, int N_T,
+                                           double* sm_axes) {
+    for (int e = threadIdx.x; e < S * N_P; e += blockDim.x) sm_axes[e] = axis_P[e];
+    for (int e = threadIdx.x; e < S * N_T; e += blockDim.x) sm_axes[S * N_P + e] = axis_T[e];
+}
+
 // Block-cooperative K0 for atmosphere b: the level records of all L levels.
-// The axes are first copied to shared memory (`sm_axes`, S (N_P + N_T) doubles; null = search in
-// global memory): the bracket search is a chain of dependent loads, ~10 L2 round trips per
-// (level, species) when the nodes are read from global memory — it was half of the 26 us of the
-// kernel that follows every sweep.  One thread per (level, species) pair, then one per level
-// for the scalars and the same-cell flag.  Callers that have just written T synchronise first;
-// this function ends with all records written (no trailing barrier).
-__device__ __forceinline__ void prep_block(const PrepArgs& a, int b, double* sm_axes) {
+// The bracket search is a chain of dependent loads, ~10 L2 round trips per (level, species) when
+// the nodes are read from global memory — it was half of the 26 us of the kernel that follows
+// every sweep — so the axes are searched in shared memory (`sm_axes`, filled by stage_axes and
+// synchronised by the caller; null = search in global memory).  One thread per (level, species)
+// pair, then one per level for the scalars and the same-cell flag.  Callers that have just
+// written T synchronise first; this function ends with all records written (no trailing barrier).
+__device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const double* sm_axes, const LevelView& lv) {
     const int L = a.L, S = a.S;
-    const double* axP = a.axis_P;
-    const double* axT = a.axis_T;
-    if (sm_axes) {
-        for (int e = threadIdx.x; e < S * a.N_P; e += blockDim.x) sm_axes[e] = a.axis_P[e];
-        for (int e = threadIdx.x; e < S * a.N_T; e += blockDim.x) sm_axes[S * a.N_P + e] = a.axis_T[e];
-        axP = sm_axes; axT = sm_axes + S * a.N_P;
-        __syncthreads();
-    }
-    const double* T = a.T + (int64_t)b * L;
-    const double* P = a.P + (int64_t)b * L;
+    const double* axP = sm_axes ? sm_axes : a.axis_P;
+    const double* axT = sm_axes ? sm_axes + S * a.N_P : a.axis_T;
+    const double* T = lv.T;
+    const double* P = lv.P;
     for (int idx = threadIdx.x; idx < L * S; idx += blockDim.x) {
         const int i = idx / S, s = idx - i * S;
         const int64_t li = (int64_t)b * L + i;
@@ -150,14 +167,15 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, double* sm_
             wt = (vt - xt[it]) / (xt[it + 1] - xt[it]);
             out = out || (vt < xt[0]) || (vt > xt[a.N_T - 1]);
         }
-        const double m = a.mmr[li * S + s];
+        const double m = lv.mmr[idx];
         double w00 = (1.0 - wp) * (1.0 - wt), w01 = (1.0 - wp) * wt;
         double w10 = wp * (1.0 - wt), w11 = wp * wt;
         if (out) { w00 = w01 = w10 = w11 = 0.0; }       // fill_value=0, opacity.py:243
         double* W = rec + 2 + 4 * s;
         W[0] = m * w00; W[1] = m * w01; W[2] = m * w10; W[3] = m * w11;
-        reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s] =
-            (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
+        const int64_t off = (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
+        reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s] = off;
+        if (lv.off) lv.off[idx] = off;
         if (a.iP) a.iP[li * S + s] = ip;
         if (a.iT) a.iT[li * S + s] = it;
         if (a.wP) a.wP[li * S + s] = wp;
@@ -179,8 +197,9 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, double* sm_
         int64_t same = 0;
         if (i > 0) {
             same = 1;
-            const int64_t* o1 = reinterpret_cast<const int64_t*>(rec) + 2 + 4 * S;
-            const int64_t* o0 = o1 - a.lp.rec8;
+            const int64_t* o1 = lv.off ? lv.off + (int64_t)i * S
+                                       : reinterpret_cast<const int64_t*>(rec) + 2 + 4 * S;
+            const int64_t* o0 = lv.off ? o1 - S : o1 - a.lp.rec8;
             for (int s = 0; s < S; ++s) if (o0[s] != o1[s]) same = 0;
         }
         reinterpret_cast<int64_t*>(rec)[2 + 5 * S] = same;
@@ -195,7 +214,12 @@ static inline size_t prep_axes_bytes(int S, int N_P, int N_T) {
 
 __global__ void prep_kernel(PrepArgs a, int use_smem) {
     extern __shared__ double sm_prep[];
-    prep_block(a, blockIdx.x, use_smem ? sm_prep : nullptr);
+    if (use_smem) {
+        stage_axes(a.axis_P, a.axis_T, a.S, a.N_P, a.N_T, sm_prep);
+        __syncthreads();
+    }
+    prep_block(a, blockIdx.x, use_smem ? sm_prep : nullptr,
+               global_levels(a.T, a.P, a.mmr, blockIdx.x, a.L, a.S));
 }
 
 // ---------------------------------------------------------------------------
@@ -399,6 +423,41 @@ __device__ __forceinline__ void two_stream_tail(double dtau, double w0, double o
     F1d = fma(ic, fma(psi, F2d, -xi * F1u), pc * fma(B1, A, -H));       // :169-176
 }
 
+// Layer response for omega0 < 0.1 (E = 1, twostream.py:89-94), taken when the warp vote finds no
+// lane that needs Deitrick's correction.  With E = 1 the reference's expressions collapse further:
+//   s = sigma + k,  1 - omega0 = k / s,  r = sqrt(1 - omega0) = k y  with  y = 1 / sqrt(k s)
+//   omega0 = sigma / s = sigma (r y)            (one rsqrt replaces the reciprocal AND the sqrt)
+//   pi (1 - omega0) / (E - omega0) / chi = pi / chi     (no second factor to carry, :152)
+// which is 8 fp64 instructions and one MUFU fewer per evaluation than the general form.  The
+// results agree with the general form to rounding (~1e-16 relative), not bit for bit.
+// dpg2 = 2 (p1 - p2)/g.
+__device__ __forceinline__ void two_stream_E1(double k, double sg, double dpg2, double F1u, double F2d,
+                                              double B1, double B2, const double* tab, double& F2u,
+                                              double& F1d) {
+    const double s = sg + k;
+    double y;
+    (void)fast_sqrt(k * s, y);                                          // y = 1/sqrt(k s)
+    const double r = k * y;                                             // sqrt((E - w0)/E), :143
+    const double w0 = sg * (r * y);                                     // omega0, :376-378
+    const double u = r * (dpg2 * k);                                    // T = exp(-u), :139
+    double Tr, m, uq;
+    bool small;
+    exp_neg(u, tab, Tr, m, uq, small);
+    const double opr = 1.0 + r;
+    const double R2 = fast_rcp(opr * u);
+    const double z = 0.5 * w0 * (u * R2);                               // zeta_minus, :145
+    const double e1 = small ? uq : fma(-(m * opr), R2, 1.0);            // 1 - m/u
+    const double zm = z * m, omzm = 1.0 - zm;
+    const double chi = -(r + zm) * omzm;                                // :149
+    const double xi = (1.0 - z) * zm * (2.0 - m);                       // :150
+    const double psi = -r * Tr;                                         // :151
+    const double A = fma(2.0, xi, -m * omzm);                           // chi + xi - psi
+    const double H = (B1 - B2) * r * fma(zm, 1.0 - e1, e1 - m);         // psi D + B'/(2E)(chi-psi-xi)
+    const double ic = fast_rcp(chi);
+    F2u = ic * fma(FREI_PI, fma(B2, A, H), fma(psi, F1u, -xi * F2d));   // :161-168
+    F1d = ic * fma(FREI_PI, fma(B1, A, -H), fma(psi, F2d, -xi * F1u));  // :169-176
+}
+
 __device__ __forceinline__ void two_stream_k(double k, double sg, double dpg, double F1u, double F2d,
                                              double B1, double B2, const double* tab, double& F2u,
                                              double& F1d, double& dtau) {
@@ -589,6 +648,21 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
                                             const double* sg, double* k) {
     const int SS = (S_T > 0) ? S_T : S;
     constexpr int kRowElems = kThreads * V;
+#ifdef EXP_NO_GATHER                  // timing experiment only (wrong results): one row instead of 4 S
+    {
+        double t0[V];
+        SVec<V>::ld(slot, t0);
+#pragma unroll
+        for (int v = 0; v < V; ++v) k[v] = fma(t0[v], rec[2], sg[v]);
+        return;
+    }
+#endif
+    // two accumulation chains (corners 0, 1 starting from sigma; corners 2, 3), joined at the end:
+    // 4 S + 1 fp64 instructions with a dependent depth of 2 S + 1 (the reference adds the species
+    // left to right, opacity.py:265-269; the difference is rounding in the last place)
+    double ka[V], kb[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) { ka[v] = sg[v]; kb[v] = 0.0; }          // k includes sigma, opacity.py:269
 #pragma unroll 4
     for (int s = 0; s < SS; ++s) {
         const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
@@ -600,15 +674,14 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
         SVec<V>::ld(slot + (4 * s + 3) * kRowElems, t3);
 #pragma unroll
         for (int v = 0; v < V; ++v) {
-            double x = t0[v] * wa.x;
-            x = fma(t1[v], wa.y, x);
-            x = fma(t2[v], wb.x, x);
-            x = fma(t3[v], wb.y, x);
-            k[v] = (s == 0) ? x : k[v] + x;      // left-to-right sum over species, opacity.py:265-268
+            ka[v] = fma(t0[v], wa.x, ka[v]);
+            ka[v] = fma(t1[v], wa.y, ka[v]);
+            kb[v] = fma(t2[v], wb.x, kb[v]);
+            kb[v] = fma(t3[v], wb.y, kb[v]);
         }
     }
 #pragma unroll
-    for (int v = 0; v < V; ++v) k[v] += sg[v];            // k includes sigma, opacity.py:269
+    for (int v = 0; v < V; ++v) k[v] = ka[v] + kb[v];
 }
 
 // Per-thread state of the sweep: V wavelengths.
@@ -616,35 +689,43 @@ template <int V>
 struct Lane {
     double c1[V], c2[V], sg[V], wj[V];
     double Fcar[V], Bcar[V];     // carried stream (F_up for emit, F_down for absorb) and Planck term
+    int thr[V];                  // high word of 9 sigma (1 + 2^-18): k above it has omega0 < 0.1 for certain
 };
 
-// second half of a layer-step (after the vote on omega0): Planck term of the new level, the
-// two-stream response, the four wavelength-integral contributions
+// One layer-step for V wavelengths after the warp vote: Planck term of the new level, the
+// two-stream response (general form or the E = 1 form), the four wavelength-integral contributions.
 template <int DIR, int V, bool SAME_T, bool E_IS_ONE>
-__device__ __forceinline__ void layer_tail(Lane<V>& t, const double* w0, const double* omw, const double* other,
+__device__ __forceinline__ void layer_tail(Lane<V>& t, const double* k, double dpg, const double* other,
                                            double invTn, const double* tab, double* F2u, double* F1d,
-                                           const double* dtau, double* red) {
+                                           double* dtau, double* red) {
     red[0] = red[1] = red[2] = red[3] = 0.0;
+    const double dpg2 = dpg + dpg;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
+#ifdef EXP_NO_PLANCK                  // timing experiment only (wrong results): no Planck evaluation
+        const double Bn = t.Bcar[v] + invTn;
+#else
         const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn, tab);
-        if (DIR == FREI_EMIT) {          // carried = F_1_up, B_1; other = F_2_down; new B = B_2
-            two_stream_tail<E_IS_ONE>(dtau[v], w0[v], omw[v], t.Fcar[v], other[v], t.Bcar[v], Bn, tab,
-                                      F2u[v], F1d[v]);
-            red[0] = fma(t.wj[v], F2u[v], red[0]);
-            red[1] = fma(t.wj[v], other[v], red[1]);
-            red[2] = fma(t.wj[v], t.Fcar[v], red[2]);
-            red[3] = fma(t.wj[v], F1d[v], red[3]);
-            t.Fcar[v] = F2u[v];
-        } else {                         // carried = F_2_down, B_2; other = F_1_up; new B = B_1
-            two_stream_tail<E_IS_ONE>(dtau[v], w0[v], omw[v], other[v], t.Fcar[v], Bn, t.Bcar[v], tab,
-                                      F2u[v], F1d[v]);
-            red[0] = fma(t.wj[v], F2u[v], red[0]);
-            red[1] = fma(t.wj[v], t.Fcar[v], red[1]);
-            red[2] = fma(t.wj[v], other[v], red[2]);
-            red[3] = fma(t.wj[v], F1d[v], red[3]);
-            t.Fcar[v] = F1d[v];
+#endif
+        dtau[v] = dpg * k[v];                                            // :371-373 (dead unless DTAUS)
+        // emit: carried = F_1_up, B_1; other = F_2_down; new B = B_2
+        // absorb: carried = F_2_down, B_2; other = F_1_up; new B = B_1
+        const double F1u = (DIR == FREI_EMIT) ? t.Fcar[v] : other[v];
+        const double F2d = (DIR == FREI_EMIT) ? other[v] : t.Fcar[v];
+        const double B1 = (DIR == FREI_EMIT) ? t.Bcar[v] : Bn;
+        const double B2 = (DIR == FREI_EMIT) ? Bn : t.Bcar[v];
+        if (E_IS_ONE) {
+            two_stream_E1(k[v], t.sg[v], dpg2, F1u, F2d, B1, B2, tab, F2u[v], F1d[v]);
+        } else {
+            double w0, omw, dt;
+            two_stream_front(k[v], t.sg[v], dpg, dt, w0, omw);
+            two_stream_tail<false>(dt, w0, omw, F1u, F2d, B1, B2, tab, F2u[v], F1d[v]);
         }
+        red[0] = fma(t.wj[v], F2u[v], red[0]);
+        red[1] = fma(t.wj[v], F2d, red[1]);
+        red[2] = fma(t.wj[v], F1u, red[2]);
+        red[3] = fma(t.wj[v], F1d[v], red[3]);
+        t.Fcar[v] = (DIR == FREI_EMIT) ? F2u[v] : F1d[v];
         t.Bcar[v] = Bn;
     }
 }
@@ -653,27 +734,24 @@ __device__ __forceinline__ void layer_tail(Lane<V>& t, const double* w0, const d
 // 1/T of the level whose Planck term is new this step (ignored when SAME_T: emit's top
 // pseudo-layer has T_2 = T_1, twostream.py:358-363).  Writes the two outgoing streams, the four
 // wavelength-integral contributions of this thread, and delta_tau.  The warp votes on
-// omega0 > 0.1 and takes the E = 1 specialisation when no lane needs the general form.
+// omega0 > 0.1 before any division — omega0 = sigma / (sigma + k) > 0.1  <=>  k < 9 sigma, tested
+// on the high words against the per-wavelength threshold t.thr (a superset: the general form is
+// correct for every omega0, so a false positive only costs time) — and takes the E = 1 form when
+// no lane needs the general one.
 template <int DIR, int V, bool SAME_T>
 __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double dpg, const double* other,
                                            double invTn, const double* tab, double* F2u, double* F1d,
                                            double* dtau, double* red) {
-    double w0[V], omw[V];
+#if SWEEP_E_VOTE
     bool hi = false;
 #pragma unroll
-    for (int v = 0; v < V; ++v) {
-        two_stream_front(k[v], t.sg[v], dpg, dtau[v], w0[v], omw[v]);
-        // conservative test on the high word (omega0 >= 0.0999999..., 0x3FB99999 = high word of
-        // 0.1): the general form is correct for every omega0, so a superset only costs time
-        hi = hi || (__double2hiint(w0[v]) >= 0x3FB99999);
-    }
-#if SWEEP_E_VOTE
+    for (int v = 0; v < V; ++v) hi = hi || (__double2hiint(k[v]) <= t.thr[v]);
     if (__any_sync(0xffffffffu, hi))
-        layer_tail<DIR, V, SAME_T, false>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+        layer_tail<DIR, V, SAME_T, false>(t, k, dpg, other, invTn, tab, F2u, F1d, dtau, red);
     else
-        layer_tail<DIR, V, SAME_T, true>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+        layer_tail<DIR, V, SAME_T, true>(t, k, dpg, other, invTn, tab, F2u, F1d, dtau, red);
 #else
-    layer_tail<DIR, V, SAME_T, false>(t, w0, omw, other, invTn, tab, F2u, F1d, dtau, red);
+    layer_tail<DIR, V, SAME_T, false>(t, k, dpg, other, invTn, tab, F2u, F1d, dtau, red);
 #endif
 }
 
@@ -688,7 +766,7 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 // basic block (no data-dependent or uniform branches) and there is no CTA barrier after the
 // staging: warps run their chunks independently.
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MINB) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) ? 2 : SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double tab[32];                   // 2^(j/32) for exp_neg
@@ -757,7 +835,11 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     Vec<V>::ldg(a.sigma + j, t.sg);
     Vec<V>::ldg(a.w + j, t.wj);
 #pragma unroll
-    for (int v = 0; v < V; ++v) { t.sg[v] *= sscale; if (!live) t.wj[v] = 0.0; }
+    for (int v = 0; v < V; ++v) {
+        t.sg[v] *= sscale;
+        if (!live) t.wj[v] = 0.0;
+        t.thr[v] = __double2hiint(t.sg[v] * 9.00003433227539062) + 1;    // 9 (1 + 2^-18)
+    }
     if (DTAUS && live) {                         // leading row of ones, twostream.py:352/:487
         double one[V];
 #pragma unroll
@@ -775,8 +857,12 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : SWEEP_MIN
     constexpr bool kFluxAsync = SWEEP_FLUX_ASYNC, kDeferRed = SWEEP_DEFER_RED;
     uint32_t fcur = fstage, fnxt = fstage + (uint32_t)(kThreads * V * sizeof(double));
     auto publish = [&](const double* r, int row) {
+#ifdef EXP_NO_REDUCE                  // timing experiment only (wrong results): no warp reduction
+        if (lane == 0) { part[row * 4] = r[0] + r[1]; part[row * 4 + 2] = r[2] + r[3]; }
+#else
         const double r4 = warp_reduce4(r[0], r[1], r[2], r[3], lane);
         if ((lane & 7) == 0) part[row * 4 + (lane >> 3)] = r4;
+#endif
     };
     if (DIR == FREI_EMIT) {
         // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
@@ -919,12 +1005,11 @@ struct UpdateArgs {
 
 // dT of level i of atmosphere b from its four wavelength integrals s[0..3]
 // (div_bol_net_flux, convective_flux, delta_t_i, delta_temperature; twostream.py:23-43, 190-287)
-__device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int i, const double* s) {
+__device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int i, const double* s,
+                                                const double* Tb, const double* Pb) {
     const int L = u.L;
     const bool active = (u.direction == FREI_EMIT) ? (i >= 1) : (i <= L - 2);
     if (!active) return 0.0;                                  // dT[0] = 0 (emit), dT[L-1] = 0 (absorb)
-    const double* Tb = u.T + (int64_t)b * L;
-    const double* Pb = u.P + (int64_t)b * L;
     const double T1 = Tb[i];
     const double g = u.g[b], m_bar = u.m_bar[b];
     const double alpha = (u.alpha_override >= 0.0) ? u.alpha_override : u.alpha[b];
@@ -959,20 +1044,25 @@ __device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int 
 }
 
 // Block-wide: thread i = level i.  All reads of T precede the barrier, all writes follow it;
-// then (optionally) the records of the new T are rebuilt for the next sweep.
+// then (optionally) the records of the new T are rebuilt for the next sweep.  `lv` = where T, P
+// and the mixing ratios of this atmosphere are read; `sm_T` (nullable) = a writable shared-memory
+// copy of T that lv.T points to: the new T is stored there as well, so K0 does not wait for a
+// global-memory round trip of what this block has just computed.
 __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepArgs& pa, int do_prep,
-                                                int b, const double* sums_b, double* sm_axes) {
+                                                int b, const double* sums_b, const double* sm_axes,
+                                                const LevelView& lv, double* sm_T) {
     const int i = threadIdx.x, L = u.L;
     double dT = 0.0, T1 = 0.0;
     if (i < L) {
-        T1 = u.T[(int64_t)b * L + i];
-        dT = delta_T_level(u, b, i, sums_b + i * 4);
+        T1 = lv.T[i];
+        dT = delta_T_level(u, b, i, sums_b + i * 4, lv.T, lv.P);
     }
     __syncthreads();
     const double Tn = T1 - dT;                                                // :407, :536
     if (i < L) {
         u.dT[(int64_t)b * L + i] = dT;
         u.T[(int64_t)b * L + i] = Tn;
+        if (sm_T) sm_T[i] = Tn;
         if (u.T_hist) u.T_hist[(int64_t)b * L + i] = Tn;
     }
     if (u.trk_T) {
@@ -1008,15 +1098,17 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
     }
     if (!do_prep) return;
     __syncthreads();
-    prep_block(pa, b, sm_axes);
+    prep_block(pa, b, sm_axes, lv);
 }
 
 __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums,
                                    int use_smem) {
     extern __shared__ double sm_upd[];
     if (u.active && !u.active[blockIdx.x]) return;
+    if (do_prep && use_smem) stage_axes(pa.axis_P, pa.axis_T, pa.S, pa.N_P, pa.N_T, sm_upd);   // synchronised inside
     update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4,
-                    use_smem ? sm_upd : nullptr);
+                    (do_prep && use_smem) ? sm_upd : nullptr,
+                    global_levels(u.T, u.P, do_prep ? pa.mmr : nullptr, blockIdx.x, u.L, pa.S), nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1037,19 +1129,37 @@ struct PostArgs {
     int rank, world, B;
     int rows, rows_per_chunk, nchunks;
     int do_update, do_prep;
-    int axes_smem;                       // the axes of K0 fit behind the sums in shared memory
+    int axes_smem;                       // the axes of K0 are searched in shared memory
+    int stage_levels;                    // T, P, mmr (and the row offsets) of the atmosphere are staged in shared memory
 };
 
 // Sum `count` rows of n doubles (row stride n) element-wise with all threads of the CTA:
-// thread (g, e) adds rows g, g + G, ... of element e (independent loads), then the G group
-// results are added in group order through shared memory.  Fixed order -> deterministic.
+// thread (g, e) adds rows g, g + G, ... of element e, then the G group results are added in
+// group order through shared memory.  Fixed order -> deterministic.  The loads of a thread are
+// issued kBatch at a time before the first addition (the additions keep their order): the second
+// stage of the reduction reads ~150 rows with 5 groups, and as a chain of dependent
+// load-then-add steps it cost ~5 us of L2 latency on the critical path of every sweep.
 __device__ __forceinline__ double cta_column_sum(const double* __restrict__ rows, int count, int n,
                                                  double* scratch /* [G][n] */, int G) {
+    constexpr int kBatch = 16;
     const int e = threadIdx.x % n, g = threadIdx.x / n;
     double s = 0.0;
     if (g < G) {
-#pragma unroll 4
-        for (int r = g; r < count; r += G) s += rows[(int64_t)r * n + e];
+        int r = g;
+        for (; r + (kBatch - 1) * G < count; r += kBatch * G) {
+            double v[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) v[k] = rows[(int64_t)(r + k * G) * n + e];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) s += v[k];
+        }
+        {
+            double v[kBatch];
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) v[k] = (r + k * G < count) ? rows[(int64_t)(r + k * G) * n + e] : 0.0;
+#pragma unroll
+            for (int k = 0; k < kBatch; ++k) if (r + k * G < count) s += v[k];
+        }
         scratch[g * n + e] = s;
     }
     __syncthreads();
@@ -1060,15 +1170,39 @@ __device__ __forceinline__ double cta_column_sum(const double* __restrict__ rows
     return tot;              // valid in threads with g == 0 (threadIdx.x < n)
 }
 
-__global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
-    extern __shared__ double sm_post[];          // [G][n] scratch, then [n] sums
+// Shared memory of post_kernel, in doubles: [G n] scratch, [n] sums, then (do_update) T[L], P[L],
+// then (do_prep) mmr[L S], off[L S], axes[S (N_P + N_T)].
+__global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
+    extern __shared__ double sm_post[];
     __shared__ int is_last;
-    const int b = blockIdx.y, chunk = blockIdx.x, n = u.L * 4;
+    const int b = blockIdx.y, chunk = blockIdx.x, n = u.L * 4, L = u.L;
+    const int G = blockDim.x / n;                // row groups per CTA (>= 1, host guarantees)
+    double* sm_sums = sm_post + (size_t)G * n;
+    const int Lst = q.stage_levels ? L : 0;      // level areas are empty when they do not fit
+    double* sm_T = sm_sums + n;
+    double* sm_P = sm_T + Lst;
+    double* sm_mmr = sm_P + Lst;
+    int64_t* sm_off = reinterpret_cast<int64_t*>(sm_mmr + (size_t)Lst * pa.S);
+    double* sm_axes = reinterpret_cast<double*>(sm_off + (size_t)Lst * pa.S);
+    // Everything the serial tail needs that the sweep does not write — T (last written by the
+    // previous post kernel, which completed before the sweep in front of us got past its own
+    // griddepcontrol.wait), P, the mixing ratios, the table axes — is copied to shared memory
+    // BEFORE waiting for the sweep: with programmatic dependent launch these CTAs are resident
+    // while the sweep drains, so the loads overlap its tail instead of following it.  Any CTA may
+    // turn out to be the last one of its atmosphere, so all of them do it (a few KB each).
+    if (q.stage_levels) {
+        if (q.do_update)
+            for (int e = threadIdx.x; e < L; e += blockDim.x) {
+                sm_T[e] = u.T[(int64_t)b * L + e];
+                sm_P[e] = u.P[(int64_t)b * L + e];
+            }
+        if (q.do_prep)
+            for (int e = threadIdx.x; e < L * pa.S; e += blockDim.x) sm_mmr[e] = pa.mmr[(int64_t)b * L * pa.S + e];
+    }
+    if (q.do_prep && q.axes_smem) stage_axes(pa.axis_P, pa.axis_T, pa.S, pa.N_P, pa.N_T, sm_axes);
     pdl_wait();                                  // partials come from the sweep before
     pdl_launch_dependents();                     // the next sweep's CTAs may line up behind the serial tail
     if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
-    const int G = blockDim.x / n;                // row groups per CTA (>= 1, host guarantees)
-    double* sm_sums = sm_post + (size_t)G * n;
     const int r0 = chunk * q.rows_per_chunk, r1 = min(q.rows, r0 + q.rows_per_chunk);
     const double* p = q.partials + ((int64_t)b * q.rows + r0) * n;
     const double s1 = cta_column_sum(p, r1 - r0, n, sm_post, G);
@@ -1124,7 +1258,11 @@ __global__ void post_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
     if (threadIdx.x == 0) q.counters[b] = 0u;    // self-cleaning for the next launch
     if (!q.do_update) return;
     __syncthreads();
-    update_and_prep(u, pa, q.do_prep, b, sm_sums, q.axes_smem ? sm_sums + n : nullptr);
+    LevelView lv;
+    if (q.stage_levels) { lv.T = sm_T; lv.P = sm_P; lv.mmr = sm_mmr; lv.off = sm_off; }
+    else lv = global_levels(u.T, u.P, q.do_prep ? pa.mmr : nullptr, b, L, pa.S);
+    update_and_prep(u, pa, q.do_prep, b, sm_sums, (q.do_prep && q.axes_smem) ? sm_axes : nullptr, lv,
+                    q.stage_levels ? sm_T : nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1152,7 +1290,13 @@ static int num_sms() {
     return g_num_sms;
 }
 
-static inline int sweep_V(int64_t n_lam) { return (n_lam % 2 != 0) ? 1 : 2; }
+#ifndef SWEEP_V4
+#define SWEEP_V4 0                // experiment knob: 4 wavelengths per thread (2 CTAs/SM) when n_lam % 4 == 0
+#endif
+static inline int sweep_V(int64_t n_lam) {
+    if (SWEEP_V4 && n_lam % 4 == 0) return 4;
+    return (n_lam % 2 != 0) ? 1 : 2;
+}
 static inline int sweep_rows(int64_t n_lam, int /*B*/) {
     const int64_t per_cta = (int64_t)kThreads * sweep_V(n_lam);
     return (int)((n_lam + per_cta - 1) / per_cta) * kWarps;
@@ -1187,6 +1331,11 @@ static int launch_sweep_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
 
 template <typename TabT, int S_T, int DIR>
 static int launch_sweep_v(const SweepArgs& a, int V, size_t smem, cudaStream_t st) {
+#if SWEEP_V4
+    if (V == 4)
+        return a.dtaus ? launch_sweep_one<TabT, S_T, DIR, 4, true>(a, smem, st)
+                       : launch_sweep_one<TabT, S_T, DIR, 4, false>(a, smem, st);
+#endif
     if (a.dtaus)
         return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, smem, st)
                       : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, smem, st);
@@ -1382,7 +1531,11 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     ARG_TRY(atm->L >= 3 && atm->L <= 256 && atm->B <= 65535);
     PostArgs q;
     q.rows = sweep_rows(n_lam, atm->B);
-    q.nchunks = q.rows < kPostChunks ? q.rows : kPostChunks;
+    // Two reduction stages of about sqrt(rows) rows each keep the dependent load batches of both
+    // short (C1: 9 chunks, C2: 56, C3 on one GPU: 125); at most kPostChunks, the workspace layout's bound.
+    q.nchunks = (int)ceil(sqrt((double)q.rows));
+    if (q.nchunks > kPostChunks) q.nchunks = kPostChunks;
+    if (q.nchunks < 1) q.nchunks = 1;
     q.rows_per_chunk = (q.rows + q.nchunks - 1) / q.nchunks;
     q.nchunks = (q.rows + q.rows_per_chunk - 1) / q.rows_per_chunk;
     const int64_t n = (int64_t)atm->L * 4;
@@ -1422,8 +1575,12 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     const int threads = (G * (int)n + 31) / 32 * 32;
     const size_t axes = do_prep ? prep_axes_bytes(tab->S, tab->N_P, tab->N_T) : 0;
     q.axes_smem = axes > 0;
-    CUDA_TRY(launch_pdl(post_kernel, dim3(q.nchunks, atm->B), dim3(threads),
-                        (size_t)(G + 1) * n * sizeof(double) + axes, st, q, u, pa));
+    // T, P (update) and mmr, row offsets (K0) of the atmosphere, staged before the wait on the sweep
+    const size_t levels = do_update ? (size_t)atm->L * (2 + (do_prep ? 2 * tab->S : 0)) * sizeof(double) : 0;
+    size_t smem = (size_t)(G + 1) * n * sizeof(double) + axes;
+    q.stage_levels = (levels > 0 && smem + levels <= 48 * 1024) ? 1 : 0;
+    if (q.stage_levels) smem += levels;
+    CUDA_TRY(launch_pdl(post_kernel, dim3(q.nchunks, atm->B), dim3(threads), smem, st, q, u, pa));
     return FREI_OK;
 }
 
