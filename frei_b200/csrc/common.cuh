@@ -18,8 +18,8 @@
 #define SWEEP_THREADS 128
 #endif
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 3              // resident CTAs per SM the V = 2 sweep kernel is compiled for (<= 168 registers:
-                                  // measured 2-4 % faster than 4 CTAs at 128 registers)
+#define SWEEP_MINB 4              // resident CTAs per SM the V = 2 sweep kernel is compiled for (<= 128 registers,
+                                  // no spills; the host may launch fewer per SM, see choose_ctas_per_sm)
 #endif
 #ifndef SWEEP_MINB_V1
 #define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
@@ -119,4 +119,4 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 int frei_set_err(int code, const char* msg);
 // fp32-arithmetic sweep (sweep_f32.cu): flux state and table in fp32, wavelength integrals in fp64
-int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, cudaStream_t st);
+int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, int plan_V, cudaStream_t st);

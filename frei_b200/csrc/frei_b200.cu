@@ -1293,12 +1293,18 @@ static int num_sms() {
 #ifndef SWEEP_V4
 #define SWEEP_V4 0                // experiment knob: 4 wavelengths per thread (2 CTAs/SM) when n_lam % 4 == 0
 #endif
-static inline int sweep_V(int64_t n_lam) {
+// Wavelengths per thread.  V = 1 for odd counts, and for problems so small that V = 2 would leave
+// SMs without a warp (fewer than two chunks of 64 per SM over the whole batch, e.g. C1's 5k bins =
+// 79 chunks on 148 SMs): a chunk is a serial recurrence, so halving it is the only parallelism left.
+static int g_force_V = 0;          // test hook (frei_b200_debug_plan): 0 = automatic
+static inline int sweep_V(int64_t n_lam, int B) {
+    if (n_lam % 2 != 0 || g_force_V == 1) return 1;
+    if (g_force_V != 2 && (int64_t)B * ((n_lam + 63) / 64) < 2 * (int64_t)num_sms()) return 1;
     if (SWEEP_V4 && n_lam % 4 == 0) return 4;
-    return (n_lam % 2 != 0) ? 1 : 2;
+    return 2;
 }
-static inline int sweep_rows(int64_t n_lam, int /*B*/) {
-    const int64_t per_cta = (int64_t)kThreads * sweep_V(n_lam);
+static inline int sweep_rows(int64_t n_lam, int B) {
+    const int64_t per_cta = (int64_t)kThreads * sweep_V(n_lam, B);
     return (int)((n_lam + per_cta - 1) / per_cta) * kWarps;
 }
 
@@ -1308,7 +1314,7 @@ static inline int sweep_rows(int64_t n_lam, int /*B*/) {
 
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
 static int launch_sweep_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
-    static int resident = -1;     // CTAs per SM of this instantiation (smem differs by < 1 CTA)
+    static int resident = -1;     // CTAs per SM of this instantiation at the largest shared-memory size seen
     static size_t smem_set = 0;
     auto kern = sweep_kernel<TabT, S_T, DIR, V, DTAUS>;
     if (resident < 0 || smem > smem_set) {
@@ -1320,6 +1326,9 @@ static int launch_sweep_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
         resident = nb > 0 ? nb : 1;
         smem_set = smem;
     }
+    // One resident wave for a single atmosphere, with as many CTAs per SM as fit: launching fewer
+    // to trade a nearly empty last round for fuller ones was measured (2, 3, 4 CTAs/SM at 100k ...
+    // 600k wavelengths, scripts/ctas_scan.sh) and never won — 4 CTAs/SM are 0 ... 18 % faster than 3.
     unsigned blocks = (unsigned)((a.rows - a.row0) / kWarps);
     if (SWEEP_PERSISTENT && a.B == 1) {
         const unsigned cap = (unsigned)(resident * num_sms());
@@ -1406,6 +1415,12 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
     return FREI_OK;
 }
 
+int frei_b200_debug_plan(int32_t force_V) {
+    ARG_TRY(force_V == 0 || force_V == 1 || force_V == 2);
+    g_force_V = force_V;
+    return FREI_OK;
+}
+
 int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream) {
     ARG_TRY(d_x && d_out && n > 0);
     debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n);
@@ -1482,15 +1497,15 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
     a.rows = sweep_rows(tab->n_lam, atm->B);
     a.j0 = 0; a.j1 = tab->n_lam; a.row0 = 0;
+    const int V = sweep_V(tab->n_lam, atm->B);
     if (flux->dtype == FREI_F32)                 // fp32 arithmetic: sweep_f32.cu, same partials layout
-        return frei_launch_sweep_f32(a, tab->dtype, direction, (cudaStream_t)stream);
-    const int V = sweep_V(tab->n_lam);
+        return frei_launch_sweep_f32(a, tab->dtype, direction, V, (cudaStream_t)stream);
 #ifndef SWEEP_SMEM_PAD
 #define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
 #endif
     const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
                         (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8) +
-                        (size_t)2 * kThreads * V * sizeof(double);
+                        (SWEEP_FLUX_ASYNC ? (size_t)2 * kThreads * V * sizeof(double) : 0);   // stale-stream slots
     if (smem > 200 * 1024)
         return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
     return (tab->dtype == FREI_F32) ? launch_sweep<float>(a, direction, V, smem, (cudaStream_t)stream)

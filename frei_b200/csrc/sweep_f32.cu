@@ -356,16 +356,17 @@ int launch_v(const SweepArgs& a, int direction, cudaStream_t st) {
 
 }  // namespace
 
-// The launch covers [a.j0, a.j1) with the CTA size (in wavelengths) of the fp64 plan:
-// 256 when the count is even (V = 4 x 64 threads, or V = 2 x 128 threads), else 128 (V = 1).
-int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, cudaStream_t st) {
+// The launch covers [a.j0, a.j1) with the CTA size (in wavelengths) of the fp64 plan (plan_V =
+// its wavelengths per thread): 256 when plan_V >= 2 (V = 4 x 64 threads, or V = 2 x 128 threads),
+// else 128 (V = 1: odd counts and very small problems).
+int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, int plan_V, cudaStream_t st) {
     const int64_t n = a.n_lam;
     if (table_dtype == FREI_F32) {
+        if (plan_V == 1) return launch_v<float, 1, 128>(a, direction, st);
         if (n % 4 == 0) return launch_v<float, 4, 64>(a, direction, st);
-        if (n % 2 == 0) return launch_v<float, 2, 128>(a, direction, st);
-        return launch_v<float, 1, 128>(a, direction, st);
+        return launch_v<float, 2, 128>(a, direction, st);
     }
+    if (plan_V == 1) return launch_v<double, 1, 128>(a, direction, st);
     if (n % 4 == 0) return launch_v<double, 4, 64>(a, direction, st);
-    if (n % 2 == 0) return launch_v<double, 2, 128>(a, direction, st);
-    return launch_v<double, 1, 128>(a, direction, st);
+    return launch_v<double, 2, 128>(a, direction, st);
 }

@@ -153,6 +153,12 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
  * exp(-x), 1 - exp(-x) as computed by the kernels' branch-free fp64 routines. */
 int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream);
 
+/* Test hook: wavelengths per thread of the sweep plan.  0 (default) = automatic: 2, or 1 for odd
+ * wavelength counts and for problems too small to give every SM two warps; 1 / 2 force the
+ * choice (2 only takes effect for even counts).  Process-wide; not meant for production use:
+ * it exists so that small parity cases can exercise the two-per-thread kernels. */
+int frei_b200_debug_plan(int32_t force_V);
+
 /* K0.  Bracket (P_i, T_i) of every level in every species' axes with the rule
  * of scipy.interpolate's find_indices (reached from frei/opacity.py:261-263),
  * build mmr-premultiplied corner weights (zero when out of bounds:

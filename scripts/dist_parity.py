@@ -28,12 +28,13 @@ planet = frei.Planet(a_rstar=pl['a_rstar'], m_bar=pl['m_bar'], g=pl['g'] / 100.0
                      alpha=pl['alpha'])
 
 
-def solve(group):
+def solve(group, gather='all'):
     grid = frei.Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
     grid.load_opacities(opacities=op)
-    out = grid.emission_spectrum(n_timesteps=40, group=group)
-    global used
+    out = grid.emission_spectrum(n_timesteps=40, group=group, gather=gather)
+    global used, last_grid
     used = 'p2p-fused' if grid.engine._p2p is not None else ('nccl' if group is not None else 'single')
+    last_grid = grid
     return out, grid.n_iterations
 
 
@@ -44,6 +45,18 @@ ok = (n1 == n2 and rel(s2.flux, s1.flux) < 1e-9 and np.abs(T2 - T1).max() < 1e-6
       and h1.shape == h2.shape and np.abs(h2 - h1).max() < 1e-6 and rel(d2, d1) < 1e-10)
 print(f'rank {rank}: [{used}] iterations {n1}/{n2} spectrum rel {rel(s2.flux, s1.flux):.2e} '
       f'T {np.abs(T2 - T1).max():.2e} K dtaus {rel(d2, d1):.2e} -> {"OK" if ok else "MISMATCH"}', flush=True)
+# gather='local': every rank returns its own wavelength slice; T_eff from the resident state
+g1 = frei.Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
+teff1 = float(frei.effective_temperature(g1, s1, d1, T1))
+(s3, T3, h3, d3), n3 = solve(dist.group.WORLD, gather='local')
+lo, hi = last_grid.lam_range
+diag = last_grid.diagnostics(group=dist.group.WORLD)
+ok3 = (n3 == n2 and np.array_equal(np.asarray(s3.flux), np.asarray(s2.flux)[lo:hi])
+       and np.array_equal(d3, d2[:, lo:hi]) and np.array_equal(T3, T2)
+       and np.asarray(s3.wavelength).shape[0] == hi - lo and abs(float(diag['T_eff']) - teff1) < 1e-6)
+print(f'rank {rank}: gather=local slice [{lo}, {hi}) T_eff {float(diag["T_eff"]):.6f} vs {teff1:.6f} '
+      f'-> {"OK" if ok3 else "MISMATCH"}', flush=True)
+ok = ok and ok3
 flag = torch.tensor([0 if ok else 1], device='cuda')
 dist.all_reduce(flag)
 dist.destroy_process_group()

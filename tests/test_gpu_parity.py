@@ -28,6 +28,17 @@ LD = np.longdouble
 TINY = 1e-250        # fluxes below this are denormal-range attenuated starlight
 
 
+@pytest.fixture(params=['auto', 'v2'])
+def plan(request):
+    """Sweep plan: automatic (one wavelength per thread for these small cases) and forced
+    two-per-thread (what every production-size launch uses, partly filled last chunk included)."""
+    from frei_b200 import _cabi
+    lib = _cabi.load()
+    _cabi.check(lib.frei_b200_debug_plan(2 if request.param == 'v2' else 0))
+    yield request.param
+    _cabi.check(lib.frei_b200_debug_plan(0))
+
+
 def assert_flux_parity(gpu, ref64, refx):
     """gpu ~ refx to RTOL_X; gpu ~ ref64 to 1e-6 or 2x the fp64 oracle's own error."""
     gpu = np.asarray(gpu, dtype=LD)
@@ -247,7 +258,7 @@ def _oracle_iteration(w, tabs, n_iter, table_kappa=O.kappa, wd=np.float64):
 @pytest.mark.parametrize('L,n_lam,S,f32', [(20, 1000, 1, False), (50, 5000, 3, False),
                                            (30, 777, 8, False), (24, 1333, 3, True),
                                            (16, 130, 5, False)])
-def test_sweeps_match_oracle(L, n_lam, S, f32):
+def test_sweeps_match_oracle(L, n_lam, S, f32, plan):
     """Two full emit+absorb iterations: fluxes, dtaus, integrals, dT and T after every sweep."""
     from frei_b200 import synthetic
     from frei_b200.engine import FREI_EMIT, FREI_ABSORB, FREI_F32, FREI_F64
@@ -348,7 +359,7 @@ def _one_iteration_with_arbitration(w, align_T):
 @pytest.mark.parametrize('L,n_lam,S,T_ref', [(3, 1, 1, 2400.0), (3, 2, 3, 2400.0), (4, 63, 2, 2400.0),
                                              (7, 65, 3, 2400.0), (5, 257, 8, 2400.0),
                                              (12, 510, 3, 9000.0), (12, 129, 2, 120.0)])
-def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
+def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref, plan):
     """
     Smallest legal atmosphere (3 levels), wavelength counts around the warp-chunk and CTA sizes
     (1, 2, 63, 65, 257: odd counts take the one-wavelength-per-thread kernel, the rest the
@@ -365,7 +376,7 @@ def test_ragged_sizes_and_out_of_table_levels(L, n_lam, S, T_ref):
     _one_iteration_with_arbitration(w, align_T=(T_ref != 2400.0))
 
 
-def test_scattering_dominated_mixed_warps():
+def test_scattering_dominated_mixed_warps(plan):
     """
     Mixing ratios scaled by 1e-3: Rayleigh scattering competes with absorption, omega_0 crosses
     0.1 inside the wavelength range, so warps hold lanes on both branches of E(omega_0)
@@ -511,7 +522,7 @@ def test_emit_absorb_api_host_buffers():
     assert_flux_parity(out[1], ref[1], Fd_x)
 
 
-def test_batch_atmospheres_are_independent():
+def test_batch_atmospheres_are_independent(plan):
     """B > 1: every atmosphere of a batch equals its single-atmosphere run, bit for bit."""
     from frei_b200 import synthetic
     from frei_b200.engine import Engine, FREI_EMIT, FREI_ABSORB, FREI_F64
@@ -731,7 +742,7 @@ def test_binned_opacity_from_bin_directory(tmp_path):
 
 
 @pytest.mark.parametrize('L,n_lam,S', [(50, 5000, 3), (30, 1026, 8), (24, 1333, 2)])
-def test_fp32_mode_sweeps_within_1e4(L, n_lam, S):
+def test_fp32_mode_sweeps_within_1e4(L, n_lam, S, plan):
     """
     fp32 arithmetic mode (flux state + table in fp32, integrals in fp64): per-wavelength fluxes
     within 1e-4 relative of the fp64 oracle (BASELINE.json north_star) through three RE iterations.
