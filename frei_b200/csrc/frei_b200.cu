@@ -371,12 +371,10 @@ __device__ __forceinline__ double planck(double c1, double c2, double invT, cons
 // The reference's own grouping loses up to ~4e-6 relative accuracy where delta_tau < 1e-6
 // ("conditioning"); this one tracks the exact value of the same formulas.
 // k = total opacity (includes sigma, opacity.py:269), sg = sigma, dpg = (p1 - p2)/g.
-// Split in two so that the sweep can vote on omega0 across the warp between the halves:
-// two_stream_front gives delta_tau, omega0 and 1 - omega0; two_stream_tail<E_IS_ONE> the rest.
-// E_IS_ONE = true is the specialisation for omega0 <= 0.1 (E = 1, twostream.py:89-94) in every lane
-// of the warp: it drops the quadratic, its reciprocal and the multiplications by 1 — 9 of the ~90
-// fp64 instructions and one MUFU — and produces bit-identical results to the general form for such
-// lanes (1 * x and x * 1 are exact), so the outcome does not depend on a lane's neighbours.
+// two_stream_front gives delta_tau, omega0 and 1 - omega0; two_stream_tail<E_IS_ONE> the rest
+// (E_IS_ONE = true drops the quadratic of Deitrick's E(omega0), twostream.py:89-94, its reciprocal
+// and the multiplications by 1 for callers that know omega0 <= 0.1).  The sweep uses this general
+// form only for warps in which some lane has omega0 > 0.1; all others take two_stream_E1 below.
 __device__ __forceinline__ void two_stream_front(double k, double sg, double dpg, double& dtau,
                                                  double& w0, double& omw) {
     dtau = dpg * k;                                                     // :371-373
