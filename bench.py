@@ -164,8 +164,11 @@ def run_reference(args):
         'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
         'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-        'config': {'workload': 'C2: hot Jupiter, 50 layers x 200k lambda bins, 3 species '
-                               '(H2O+CO+CH4 synthetic tables), fp64', 'bins_timed': n_lam},
+        'config': {'workload': WORKLOADS['C2'][5], 'n_layers': L_C2,
+                   'n_lambda_global': NLAM_C2 * max(1, args.gpus), 'n_species': S_C2,
+                   'table_dtype': 'f64', 'flux_dtype': 'f64',
+                   'parallelism': f'{workers} host processes, wavelength-sharded',
+                   'bins_timed': n_lam},
         'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': workers, 'kind': 'port',
                          'sample': sample},
         'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},

@@ -22,7 +22,8 @@ files (``frei/twostream.py``, ``opacity.py``, ``core.py``, ``tp.py``,
 ``chemistry.py``) executed here under dependency stubs for astropy.units, xarray,
 specutils and periodictable (``tests/golden/run_reference.py``, ``refstubs/``):
 kappa, one-step and fully converged ``emission_spectrum``, ``propagate_fluxes``,
-the layer thermodynamics and the mock chemistry agree to 1e-9 .. 1e-13.
+the layer thermodynamics, the mock chemistry and the dashboard's contribution function
+(``frei/plot.py`` run against a matplotlib stand-in) agree to 1e-9 .. 1e-13.
 
 Conventions: layer index 0 = bottom (highest pressure) (``frei/tp.py:32``);
 wavelength ascending.  Pressures are carried in bar where the reference does
@@ -574,8 +575,9 @@ def effective_temperature_milne(pressures_bar, lam_um, spec, dtaus, final_temps)
 def contribution_function(lam_um, pressures_bar, temps, dtaus):
     """
     Normalised contribution function of the dashboard, frei/plot.py:63-79, returned as the
-    reference plots it (``cf[::-1]``, level order, frei/plot.py:83).  Parity unpinned by the
-    reference: the expression sits inside a matplotlib routine with no test or fixture.
+    reference plots it (``cf[::-1]``, level order, frei/plot.py:83).  The reference has no test or
+    fixture for it; pinned to the array its own ``dashboard`` hands to ``pcolormesh`` when run
+    under a matplotlib stand-in (tests/golden/run_reference.py, case E).
     """
     dtaus = np.asarray(dtaus)
     tau = np.cumsum(dtaus[::-1], axis=0)                                   # :63

@@ -8,7 +8,7 @@ import functools
 
 import numpy as np
 
-__all__ = ['Unit', 'Quantity', 'quantity_input', 'spectral_density', 'dimensionless_unscaled']
+__all__ = ['Unit', 'Quantity', 'quantity_input', 'spectral_density', 'spectral', 'dimensionless_unscaled']
 
 
 def _dims_eq(a, b):
@@ -92,6 +92,8 @@ class Quantity(np.ndarray):
         except ValueError:
             if equivalencies is None:
                 raise
+            if isinstance(equivalencies, _Spectral):          # wavelength <-> wavenumber: 1 / lambda
+                return Quantity(1.0 / self.view(np.ndarray), self.unit ** -1).to(unit)
             return (self * equivalencies.lam).to(unit)        # F_lambda -> lambda F_lambda
         return Quantity(self.view(np.ndarray) * f, unit)
 
@@ -154,6 +156,12 @@ class Quantity(np.ndarray):
         if 'out' in kwargs:                                   # in-place ops (q += x)
             target = kwargs.pop('out')[0]
             res = self.__array_ufunc__(ufunc, method, *inputs, **kwargs)
+            if name in ('multiply', 'true_divide', 'divide') and isinstance(res, Quantity) \
+                    and isinstance(target, Quantity):
+                # astropy: q *= x and q /= x change the unit of q in place
+                target.view(np.ndarray)[...] = res.view(np.ndarray)
+                target.unit = res.unit
+                return target
             target[...] = res
             return target
         if method == 'reduce':
@@ -244,6 +252,14 @@ class _SpectralDensity:
 
 def spectral_density(lam):
     return _SpectralDensity(lam)
+
+
+class _Spectral:
+    pass
+
+
+def spectral():
+    return _Spectral()
 
 
 def quantity_input(*a, **kw):

@@ -2,8 +2,9 @@
 Executes the reference's OWN source files (frei/twostream.py, opacity.py, core.py, tp.py,
 chemistry.py under /root/reference) with the dependency stubs of tests/golden/refstubs
 (astropy.units/constants, xarray, specutils, periodictable — none installable here) and
-writes golden vectors to tests/golden/reference_run.json.  frei/phoenix.py, plot.py and
-interp.py are not on the path and are replaced by empty modules.
+writes golden vectors to tests/golden/reference_run.json.  frei/phoenix.py and interp.py are not
+on the path and are replaced by empty modules; frei/plot.py runs against a matplotlib stand-in that
+hands back the array it is asked to draw (the contribution function, frei/plot.py:63-83).
 
 The stubs are ours, so what this pins is the reference's arithmetic and control flow
 (sweep order, stale reads, top pseudo-layer, thermodynamics incl. astropy's unit algebra,
@@ -29,13 +30,14 @@ def load_reference():
     pkg = types.ModuleType('frei')
     pkg.__path__ = [os.path.join(REF, 'frei')]
     sys.modules['frei'] = pkg
-    for name, attrs in (('frei.phoenix', ['get_binned_phoenix_spectrum']), ('frei.plot', ['dashboard']),
+    for name, attrs in (('frei.phoenix', ['get_binned_phoenix_spectrum']),
                         ('frei.interp', ['groupby_bins_agg'])):
         mod = types.ModuleType(name)
         for a in attrs:
             setattr(mod, a, lambda *x, **k: (_ for _ in ()).throw(NotImplementedError(a)))
         sys.modules[name] = mod
-    mods = {m: importlib.import_module(f'frei.{m}') for m in ('tp', 'chemistry', 'opacity', 'twostream', 'core')}
+    mods = {m: importlib.import_module(f'frei.{m}')
+            for m in ('tp', 'chemistry', 'opacity', 'twostream', 'plot', 'core')}
     return mods
 
 
@@ -66,6 +68,18 @@ def main():
         final_temps=temps.to(u.K).value.tolist(), temp_hist=hist.to(u.K).value.tolist(),
         dtaus=np.asarray(dtaus)[:, idx].tolist(),
         T_eff=float(core.effective_temperature(grid, spec, dtaus, temps).to(u.K).value))
+
+    # ---- case E: the contribution function the reference's dashboard draws for case A ----
+    # (frei/plot.py:63-83 executed from the reference's own file; the matplotlib stand-in raises
+    # Captured with the arguments of ax[1].pcolormesh(lg, pg, cf[::-1], ...))
+    import matplotlib
+    try:
+        m['plot'].dashboard(grid.lam, spec.flux, 0 * spec.flux, dtaus, grid.pressures, temps, hist, op)
+        raise RuntimeError('dashboard did not reach pcolormesh')
+    except matplotlib.Captured as cap:
+        cf = np.asarray(cap.payload[2])
+    out['E'] = dict(lam_index=idx, contribution_function=cf[:, idx].tolist(),
+                    column_sums=cf.sum(axis=0)[idx].tolist())
 
     # ---- case B: full solve on a small grid (convergence rule, many iterations) ----
     grid = core.Grid(planet=planet, T_ref=2400 * u.K, n_layers=12, n_wl_bins=120)

@@ -290,3 +290,22 @@ def test_diagnostics_restatements(default_case):
     bot_tau = dtaus.sum(axis=0)
     bot = np.exp(-bot_tau) * dtaus[0] / np.expm1(O.h * O.c / O.k_B / (lam * 1e-4) / T[0])
     np.testing.assert_allclose(cf[-1] / cf[0], top / bot, rtol=1e-9)
+
+
+def test_reference_run_case_E_contribution_function(ref_run):
+    """
+    The array the reference's own frei/plot.py hands to pcolormesh (cf[::-1], plot.py:63-83),
+    captured by running dashboard() from the reference checkout against a matplotlib stand-in
+    (tests/golden/run_reference.py, case E): pins the oracle's contribution_function.  Inputs:
+    the golden dtaus / final temperatures of case A on the same sampled wavelength columns (the
+    function is column-wise independent).
+    """
+    a, e = ref_run['A'], ref_run['E']
+    assert e['lam_index'] == a['lam_index']
+    P = np.array(a['pressures_bar'])
+    lam = np.array(a['lam_um'])
+    cf = O.contribution_function(lam, P, np.array(a['final_temps']), np.array(a['dtaus']))
+    ref = np.array(e['contribution_function'])
+    assert cf.shape == ref.shape
+    np.testing.assert_allclose(cf, ref, rtol=1e-11, atol=1e-300)
+    np.testing.assert_allclose(cf.sum(axis=0), e['column_sums'], rtol=1e-13)
