@@ -274,13 +274,13 @@ class Engine:
     def set_T(self, T):
         torch = _torch()
         self._records_stale = True
-        self.T.copy_(torch.from_numpy(np.ascontiguousarray(
+        self.T.copy_(torch.from_numpy(np.array(          # np.array: a writable, contiguous copy
             np.broadcast_to(np.asarray(T, dtype=np.float64), (self.B, self.L)))))
 
     def set_mmr(self, mmr):
         torch = _torch()
         self._records_stale = True
-        self.mmr.copy_(torch.from_numpy(np.ascontiguousarray(
+        self.mmr.copy_(torch.from_numpy(np.array(
             np.broadcast_to(np.asarray(mmr, dtype=np.float64), (self.B, self.L, self.S)))))
 
     def set_fluxes(self, F_up=None, F_down=None):
