@@ -262,6 +262,24 @@ def run_ours(args):
     peak, peak_src = read_peaks()
     achieved = algo_bytes / (sweep_avg_ms * 1e-3) / 1e9
     traffic, traffic_src = read_traffic(args.workload, args.table_dtype, args.flux_dtype, world)
+    # the pipe that actually limits the fp64 kernel: executed-path SASS counts of the
+    # layer loop for S = 3, two wavelengths per thread, E = 1 form (scripts/sass_loop_mix.py):
+    # 110 DFMA + 66 DMUL + 39 DADD per warp and layer = 64 evaluations
+    fp64_info = None
+    if S == 3 and fdtype == FREI_F64:
+        sm_hz = 1.965e9
+        evals_s = (L - 1) * (hi - lo) / (sweep_avg_ms * 1e-3)
+        inst_per_eval, flops_per_eval = 215 / 64, (2 * 110 + 66 + 39) / 2
+        # pipe cycles per warp instruction: 2, or 3 with three distinct register operands (60 of the
+        # 110 DFMAs; measured, scripts/fp64_operands.cu) -> 490 cycles per warp and layer
+        pipe_cycles_per_eval = (2 * 155 + 3 * 60) / 64
+        fp64_info = {'warp_inst_per_eval': inst_per_eval, 'flops_per_eval': flops_per_eval,
+                     'achieved_tflops': evals_s * flops_per_eval / 1e12,
+                     'peak_tflops_nominal': 148 * 64 * 2 * sm_hz / 1e12,
+                     'pipe_frac': evals_s * pipe_cycles_per_eval / (148 * 4 * sm_hz),
+                     'note': 'fp64 pipe occupancy implied by the kernel time: pipe cycles of the '
+                             'issued warp instructions / (148 SMs x 4 sub-partitions x 1.965 GHz); '
+                             'ncu sm__pipe_fp64_cycles_active: 42-46 % (capture r1i)'}
 
     # e2e through the public API: Grid.emission_spectrum with host buffers
     e2e = None
@@ -336,7 +354,8 @@ def run_ours(args):
                          'kernel': 'sweep_kernel', 'kernel_avg_ms': sweep_avg_ms,
                          'kernel_launches_timed': len(sweep_ms),
                          'bytes_per_eval': bytes_per_eval,
-                         'kernel_share_of_step': 2 * sweep_avg_ms / (ms / args.steps)},
+                         'kernel_share_of_step': 2 * sweep_avg_ms / (ms / args.steps),
+                         'fp64': fp64_info},
             'cpu_baseline': cpu,
             'e2e': e2e,
             'gpu_launches': launches,
