@@ -646,15 +646,6 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
                                             const double* sg, double* k) {
     const int SS = (S_T > 0) ? S_T : S;
     constexpr int kRowElems = kThreads * V;
-#ifdef EXP_NO_GATHER                  // timing experiment only (wrong results): one row instead of 4 S
-    {
-        double t0[V];
-        SVec<V>::ld(slot, t0);
-#pragma unroll
-        for (int v = 0; v < V; ++v) k[v] = fma(t0[v], rec[2], sg[v]);
-        return;
-    }
-#endif
     // two accumulation chains (corners 0, 1 starting from sigma; corners 2, 3), joined at the end:
     // 4 S + 1 fp64 instructions with a dependent depth of 2 S + 1 (the reference adds the species
     // left to right, opacity.py:265-269; the difference is rounding in the last place)
@@ -700,11 +691,7 @@ __device__ __forceinline__ void layer_tail(Lane<V>& t, const double* k, double d
     const double dpg2 = dpg + dpg;
 #pragma unroll
     for (int v = 0; v < V; ++v) {
-#ifdef EXP_NO_PLANCK                  // timing experiment only (wrong results): no Planck evaluation
-        const double Bn = t.Bcar[v] + invTn;
-#else
         const double Bn = SAME_T ? t.Bcar[v] : planck(t.c1[v], t.c2[v], invTn, tab);
-#endif
         dtau[v] = dpg * k[v];                                            // :371-373 (dead unless DTAUS)
         // emit: carried = F_1_up, B_1; other = F_2_down; new B = B_2
         // absorb: carried = F_2_down, B_2; other = F_1_up; new B = B_1
@@ -855,12 +842,8 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
     constexpr bool kFluxAsync = SWEEP_FLUX_ASYNC, kDeferRed = SWEEP_DEFER_RED;
     uint32_t fcur = fstage, fnxt = fstage + (uint32_t)(kThreads * V * sizeof(double));
     auto publish = [&](const double* r, int row) {
-#ifdef EXP_NO_REDUCE                  // timing experiment only (wrong results): no warp reduction
-        if (lane == 0) { part[row * 4] = r[0] + r[1]; part[row * 4 + 2] = r[2] + r[3]; }
-#else
         const double r4 = warp_reduce4(r[0], r[1], r[2], r[3], lane);
         if ((lane & 7) == 0) part[row * 4 + (lane >> 3)] = r4;
-#endif
     };
     if (DIR == FREI_EMIT) {
         // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
