@@ -21,6 +21,13 @@
 #define SWEEP_MINB 4              // resident CTAs per SM the V = 2 sweep kernel is compiled for (<= 128 registers,
                                   // no spills; the host may launch fewer per SM, see choose_ctas_per_sm)
 #endif
+#ifndef SWEEP_MINB_EMIT
+#define SWEEP_MINB_EMIT SWEEP_MINB  // experiment knob: a separate register budget for the emit instantiations (under ncu
+                                  // the emit kernel is 6 % slower at 128 registers than at 158, absorb 2 % faster)
+#endif
+#ifndef SWEEP_V1_CHUNKS_PER_SM
+#define SWEEP_V1_CHUNKS_PER_SM 2  // below this many 64-wavelength chunks per SM the plan uses one wavelength per thread
+#endif
 #ifndef SWEEP_MINB_V1
 #define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
 #endif

@@ -751,7 +751,8 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 // basic block (no data-dependent or uniform branches) and there is no CTA barrier after the
 // staging: warps run their chunks independently.
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) ? 2 : SWEEP_MINB) sweep_kernel(SweepArgs a) {
+__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) ? 2 :
+                                  (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB) sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
     __shared__ double tab[32];                   // 2^(j/32) for exp_neg
@@ -1280,7 +1281,7 @@ static int num_sms() {
 static int g_force_V = 0;          // test hook (frei_b200_debug_plan): 0 = automatic
 static inline int sweep_V(int64_t n_lam, int B) {
     if (n_lam % 2 != 0 || g_force_V == 1) return 1;
-    if (g_force_V != 2 && (int64_t)B * ((n_lam + 63) / 64) < 2 * (int64_t)num_sms()) return 1;
+    if (g_force_V != 2 && (int64_t)B * ((n_lam + 63) / 64) < SWEEP_V1_CHUNKS_PER_SM * (int64_t)num_sms()) return 1;
     if (SWEEP_V4 && n_lam % 4 == 0) return 4;
     return 2;
 }
