@@ -137,3 +137,23 @@ def test_emission_spectrum_argument_errors():
         grid.emission_spectrum(gather='rank0')
     with pytest.raises(ValueError, match='emission_spectrum'):
         grid.diagnostics()
+
+
+def test_bench_helpers_without_a_gpu():
+    """bench.py's host-side pieces: committed ncu traffic entry, peak fallback, clock-sample parsing."""
+    import bench
+    traffic, src = bench.read_traffic('C2', 64, 64, 1)
+    assert traffic and 3e8 < traffic < 6e8 and 'ncu' in src
+    assert bench.read_traffic('C9', 64, 64, 1) == (None, None)
+    peak, how = bench.read_peaks()
+    assert 5000 < peak < 9000 and how
+    cs = bench.ClockSampler(0)
+    cs.proc = object.__new__(type('P', (), {'terminate': lambda s: None, 'wait': lambda s, timeout=None: 0,
+                                            'kill': lambda s: None}))
+    cs.lines = ['0, 1965, 1965, 640.2, 0x0000000000000000, Not Active, Not Active, Not Active, Not Active',
+                '0, 1800, 1965, 990.0, 0x0000000000000004, Not Active, Not Active, Not Active, Active',
+                'garbage']
+    out = cs.stop()
+    assert out['sm_mhz'] == 1882.5 and out['sm_max_mhz'] == 1965.0
+    assert out['reasons'] == ['sw_power_cap'] and out['samples'] == 2 and out['power_w_max'] == 990.0
+    assert set(bench.WORKLOADS) == {'C1', 'C2', 'C3', 'C5'}
