@@ -56,6 +56,18 @@ def test_bad_arguments_are_rejected_without_touching_the_device():
     assert lib.frei_b200_debug_math(None, None, 0, None) == -1
 
 
+def test_diagnostics_and_plan_hooks_validate_arguments():
+    lib = _cabi.load()
+    assert lib.frei_b200_diagnostics_scratch_bytes(0) == 0
+    assert lib.frei_b200_diagnostics_scratch_bytes(1) == 3 * 8
+    assert lib.frei_b200_diagnostics_scratch_bytes(200_000) == ((200_000 + 255) // 256) * 3 * 8
+    assert lib.frei_b200_diagnostics(None, None, None, None, None, None, 30, 500, None, None, None, None,
+                                     None) == -1
+    assert b'frei_b200_diagnostics' in lib.frei_b200_last_error()
+    assert lib.frei_b200_debug_plan(3) == -1
+    assert lib.frei_b200_debug_plan(2) == 0 and lib.frei_b200_debug_plan(0) == 0
+
+
 def test_no_cpu_fallback():
     """Without a CUDA device the product path refuses to run instead of falling back."""
     import torch
