@@ -829,3 +829,34 @@ def test_grid_diagnostics_from_resident_state():
                                rtol=1e-10, atol=1e-300)
     np.testing.assert_allclose(frei.contribution_function(grid, dtaus, temps), d['contribution_function'],
                                rtol=1e-13, atol=1e-300)
+
+
+def test_split_reduce_update_sequence_equals_fused_post(plan):
+    """
+    The three-call sequence of the NCCL mode on one GPU — frei_b200_sweep, frei_b200_reduce,
+    (all-reduce of ws->sums would go here,) frei_b200_update_T with the records rebuilt in the same
+    launch — against the fused frei_b200_sweep_step: same reduction order and the same update
+    code, so T, dT, the integrals and the fluxes agree to rounding after two iterations.
+    """
+    import ctypes as C
+    import torch
+    from frei_b200 import synthetic, _cabi
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB
+    w = synthetic.make_workload(20, 1000, 3)
+    fused, split = _engine(w, want_dtaus=False), _engine(w, want_dtaus=False)
+    lib = split.lib
+    st = split._stream()
+    split.layer_prep()
+    flux = split._flux_struct(False)
+    for it in range(2):
+        for direction in (FREI_EMIT, FREI_ABSORB):
+            fused.sweep(direction)
+            _cabi.check(lib.frei_b200_sweep(C.byref(split._tab), C.byref(split._spec), C.byref(split._atm),
+                                            C.byref(flux), direction, C.byref(split._ws), st))
+            _cabi.check(lib.frei_b200_reduce(C.byref(split._atm), C.byref(split._ws), split.n_lam, st))
+            _cabi.check(lib.frei_b200_update_T(C.byref(split._tab), C.byref(split._atm), C.byref(split._ws),
+                                               direction, -1.0, None, st))
+            torch.cuda.synchronize()
+            for name in ('T', 'dT', 'sums', 'F_up', 'F_down'):
+                a, b = getattr(fused, name).cpu().numpy(), getattr(split, name).cpu().numpy()
+                np.testing.assert_allclose(b, a, rtol=1e-12, atol=1e-300, err_msg=f'{name}, iteration {it}')
