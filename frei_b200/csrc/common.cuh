@@ -18,7 +18,7 @@
 #define SWEEP_THREADS 128
 #endif
 #ifndef SWEEP_MINB
-#define SWEEP_MINB 4              // resident CTAs per SM the V = 2 sweep kernel is compiled for (<= 128 registers,
+#define SWEEP_MINB 4              // resident CTAs per SM the sweep kernel is compiled for (<= 128 registers,
                                   // no spills; the host may launch fewer per SM, see choose_ctas_per_sm)
 #endif
 #ifndef SWEEP_MINB_EMIT
@@ -28,20 +28,11 @@
 #ifndef SWEEP_V1_CHUNKS_PER_SM
 #define SWEEP_V1_CHUNKS_PER_SM 2  // below this many 64-wavelength chunks per SM the plan uses one wavelength per thread
 #endif
-#ifndef SWEEP_MINB_V1
-#define SWEEP_MINB_V1 6           // same for the V = 1 kernel (tail waves, odd wavelength counts)
-#endif
-#ifndef SWEEP_FLUX_ASYNC
-#define SWEEP_FLUX_ASYNC 0        // 1: stale stream of the next layer via cp.async slots instead of registers
+#ifndef SWEEP_MIXED_TAIL
+#define SWEEP_MIXED_TAIL 1        // 1: a last round of chunks that is at most half full runs 32-wide chunks
 #endif
 #ifndef SWEEP_E_VOTE
 #define SWEEP_E_VOTE 1            // 1: warp vote selects the E = 1 specialisation of the layer step
-#endif
-#ifndef SWEEP_FLUX_LDV
-#define SWEEP_FLUX_LDV 0          // 1: register prefetch of the stale stream through a volatile asm load
-#endif
-#ifndef SWEEP_DEFER_RED
-#define SWEEP_DEFER_RED 0         // 1: warp reduction of a layer's integrals issued one iteration late
 #endif
 constexpr int kThreads = SWEEP_THREADS;  // threads per sweep CTA
 constexpr int kWarps = kThreads / 32;
@@ -78,8 +69,9 @@ struct SweepArgs {
     void* F_up; void* F_down; void* dtaus;
     double* partials;           // [B][rows][L][4], one row per sweep warp
     int64_t n_lam;
-    int64_t j0, j1;             // wavelength range [j0, j1) covered by this launch
-    int row0, rows;             // first partial row of this launch, total rows of the sweep
+    int rows;                   // partial rows of the sweep = warp-chunks (set by the launcher from its plan)
+    int n2;                     // fp64 kernel: chunks [0, n2) are 64 wavelengths wide, [n2, rows) 32 wide
+    int32_t* plan_hdr;          // workspace header: [0] = rows, written by the sweep, read by post_kernel
     int B, L, S, N_T;
 };
 
@@ -126,4 +118,4 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
 
 int frei_set_err(int code, const char* msg);
 // fp32-arithmetic sweep (sweep_f32.cu): flux state and table in fp32, wavelength integrals in fp64
-int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, int plan_V, cudaStream_t st);
+int frei_launch_sweep_f32(SweepArgs a, int table_dtype, int direction, int plan_V, cudaStream_t st);

@@ -90,6 +90,16 @@ static inline LayerParams layer_params_view(void* p, int S) {
 }
 static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
 static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + 2 * kWarps; }   // bound on the plan's rows
+// ws->partials: [B][rows_max][L][4] chunk rows | [B][kPostChunks][L][4] stage-1 sums | [B] tickets | header
+static inline double* ws_chunk_sums(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return ws->partials + (int64_t)B * sweep_rows_max(n_lam) * L * 4;
+}
+static inline unsigned int* ws_counters(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return reinterpret_cast<unsigned int*>(ws_chunk_sums(ws, B, L, n_lam) + (int64_t)B * kPostChunks * L * 4);
+}
+static inline int32_t* ws_plan_hdr(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws_counters(ws, B, L, n_lam)) + round16((int64_t)B * 4));
+}
 
 // ---------------------------------------------------------------------------
 // K0: brackets, weights, per-layer scalars
@@ -340,8 +350,15 @@ __device__ __forceinline__ void exp_neg(double u, const double* tab, double& T, 
     const double fn = tn - MAGIC;
     double r = fma(fn, -0.021660849392446835, -u);             // ln2/32 hi (36 bits: n * hi exact)
     r = fma(fn, -5.1456092446553382e-14, r);                   // ln2/32 lo
+#ifndef FREI_EXP_DEG
+#define FREI_EXP_DEG 6            // degree of the expm1 polynomial: 6 (truncation 3e-18) or 5 (2e-15; experiment)
+#endif
+#if FREI_EXP_DEG == 6
     double q = fma(1.3888888888888889e-03, r, 8.3333333333333332e-03);   // 1/6!, 1/5!
     q = fma(q, r, 4.1666666666666664e-02);                     // 1/4!
+#else
+    double q = fma(8.3333333333333332e-03, r, 4.1666666666666664e-02);   // 1/5!, 1/4!
+#endif
     q = fma(q, r, 1.6666666666666666e-01);                     // 1/3!
     q = fma(q, r, 0.5);                                        // 1/2!
     const double p = fma(r * r, q, r);                         // expm1(r)
@@ -553,31 +570,9 @@ template <> struct Vec<1> {
     static __device__ __forceinline__ void ldg(const float* p, double* o) { o[0] = (double)__ldg(p); }
     static __device__ __forceinline__ void st(double* p, const double* v) { *p = v[0]; }
 };
-template <> struct Vec<4> {
-    static __device__ __forceinline__ void ld(const double* p, double* o) {
-        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
-        const double2 s = *reinterpret_cast<const double2*>(p + 2); o[2] = s.x; o[3] = s.y;
-    }
-    static __device__ __forceinline__ void ldg(const double* p, double* o) {
-        const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
-        const double2 s = __ldg(reinterpret_cast<const double2*>(p) + 1); o[2] = s.x; o[3] = s.y;
-    }
-    static __device__ __forceinline__ void ldg(const float* p, double* o) {
-        const float4 t = __ldg(reinterpret_cast<const float4*>(p));
-        o[0] = (double)t.x; o[1] = (double)t.y; o[2] = (double)t.z; o[3] = (double)t.w;
-    }
-    static __device__ __forceinline__ void st(double* p, const double* v) {
-        *reinterpret_cast<double2*>(p) = make_double2(v[0], v[1]);
-        *reinterpret_cast<double2*>(p + 2) = make_double2(v[2], v[3]);
-    }
-};
 template <> struct Vec<2> {
     static __device__ __forceinline__ void ld(const double* p, double* o) {
-#if SWEEP_FLUX_LDV
-        asm volatile("ld.global.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "l"(p) : "memory");
-#else
         const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
-#endif
     }
     static __device__ __forceinline__ void ldg(const double* p, double* o) {
         const double2 t = __ldg(reinterpret_cast<const double2*>(p)); o[0] = t.x; o[1] = t.y;
@@ -590,13 +585,13 @@ template <> struct Vec<2> {
     }
 };
 
-// slot of (species s, corner c) for this thread: stage + (4 s + c) * kRowBytes
+// slot of (species s, corner c) for this thread: stage + (4 s + c) * kRow (bytes)
 template <typename TabT, int S_T, int V>
 __device__ __forceinline__ void stage_rows(const TabT* __restrict__ tabj, const double* rec, int S,
                                            int64_t n_lam, int64_t rowT, uint32_t stage) {
     const int SS = (S_T > 0) ? S_T : S;
     constexpr int kSlot = V * (int)sizeof(TabT);
-    constexpr uint32_t kRow = (uint32_t)kThreads * kSlot;
+    constexpr uint32_t kRow = 32u * kSlot;       // one warp's row of the staging block
     const int64_t* off = reinterpret_cast<const int64_t*>(rec) + 2 + 4 * SS;
 #pragma unroll
     for (int s = 0; s < SS; ++s) {
@@ -614,16 +609,6 @@ template <> struct SVec<1> {
     static __device__ __forceinline__ void ld(const double* p, double* o) { o[0] = *p; }
     static __device__ __forceinline__ void ld(const float* p, double* o) { o[0] = (double)*p; }
 };
-template <> struct SVec<4> {
-    static __device__ __forceinline__ void ld(const double* p, double* o) {
-        const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
-        const double2 s = *reinterpret_cast<const double2*>(p + 2); o[2] = s.x; o[3] = s.y;
-    }
-    static __device__ __forceinline__ void ld(const float* p, double* o) {
-        const float4 t = *reinterpret_cast<const float4*>(p);
-        o[0] = (double)t.x; o[1] = (double)t.y; o[2] = (double)t.z; o[3] = (double)t.w;
-    }
-};
 template <> struct SVec<2> {
     static __device__ __forceinline__ void ld(const double* p, double* o) {
         const double2 t = *reinterpret_cast<const double2*>(p); o[0] = t.x; o[1] = t.y;
@@ -633,19 +618,12 @@ template <> struct SVec<2> {
     }
 };
 
-// V doubles from a shared-memory byte address
-template <int V>
-__device__ __forceinline__ void lds_vec(uint32_t addr, double* o) {
-    if (V == 2) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr) : "memory");
-    else asm volatile("ld.shared.f64 %0, [%1];" : "=d"(o[0]) : "r"(addr) : "memory");
-}
-
 // k[v] = sigma + sum_s sum_corners W[s][c] * staged[s][c][v]   (opacity.py:261-269)
 template <typename TabT, int S_T, int V>
 __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec, int S,
                                             const double* sg, double* k) {
     const int SS = (S_T > 0) ? S_T : S;
-    constexpr int kRowElems = kThreads * V;
+    constexpr int kRowElems = 32 * V;
     // two accumulation chains (corners 0, 1 starting from sigma; corners 2, 3), joined at the end:
     // 4 S + 1 fp64 instructions with a dependent depth of 2 S + 1 (the reference adds the species
     // left to right, opacity.py:265-269; the difference is rounding in the last place)
@@ -740,77 +718,29 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 #endif
 }
 
-// A warp-chunk = 32 * V consecutive wavelengths of one atmosphere, all layers.  The grid holds at
-// most one resident wave of CTAs (host: occupancy x SM count) and warp w of CTA c takes the
-// chunks q = w * G + c, + kWarps * G, ... (G = gridDim.x), so the chunks of a partly filled last
-// round are spread evenly over the CTAs — and with them over the SMs — instead of being grabbed
-// in bulk by whichever SMs drain first.  Each thread carries the running stream (F_up for emit,
-// F_down for absorb) and the Planck term of the shared level in registers; the other stream is
-// read stale from HBM one layer ahead of its use and both are written back.  The level records
-// are staged into shared memory by one TMA bulk copy per CTA.  The layer loop body is a single
-// basic block (no data-dependent or uniform branches) and there is no CTA barrier after the
-// staging: warps run their chunks independently.
+// A warp-chunk = 32 * V consecutive wavelengths of one atmosphere, all layers.  Each thread carries
+// the running stream (F_up for emit, F_down for absorb) and the Planck term of the shared level in
+// registers; the other stream is read stale from HBM one layer ahead of its use and both are
+// written back.  The layer loop body is a single basic block (no data-dependent or uniform
+// branches) and there is no CTA barrier: warps run their chunks independently.
+// `jbase` = first wavelength of the chunk, `part` = its [L][4] row of wavelength-integral partials.
 template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-__global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) ? 2 :
-                                  (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB) sweep_kernel(SweepArgs a) {
-    extern __shared__ __align__(16) double smem[];
-    __shared__ __align__(8) uint64_t bar;
-    __shared__ double tab[32];                   // 2^(j/32) for exp_neg
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int b = blockIdx.y;
-    pdl_wait();                                  // records, T, active flags come from the previous kernel
-    if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: post_kernel may queue up behind it
-    if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
+__device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t jbase, double* part,
+                                            const double* sm_rec, const void* sm_rows, const double* tab,
+                                            double sscale, double fscale) {
+    const int tid = threadIdx.x, lane = tid & 31;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
     const int SS = (S_T > 0) ? S_T : S;
-    if (tid < 32) tab[tid] = kExp2Tab[tid];
-    double* sm_rec = smem;                       // [L][rec8]
-    const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
-    const uint32_t stage = smem_u32(slot);       // [4 S][kThreads][V] staged table elements
-    // [2][kThreads][V] doubles behind the table slots: the stale stream of the next layer
-    const uint32_t fstage = smem_u32(reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) +
-                                     (size_t)4 * SS * kThreads * V) + (uint32_t)(tid * V * sizeof(double));
     const int64_t n_lam = a.n_lam;
-
-    // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
-    const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
-    if (tid == 0) {
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (tid == 0) {
-        const double* src = a.lp.rec + (int64_t)b * L * rec8;
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
-                     ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
-    }
     const int64_t rowT = (int64_t)a.N_T * n_lam;
-    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
-    const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
-    {   // ---- wait for the records ----
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile("{\n\t.reg .pred p;\n\t"
-                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                         "selp.u32 %0, 1, 0, p;\n\t}"
-                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
-        }
-    }
-
-  const int G = gridDim.x;
-  for (int q = warp * G + blockIdx.x; q < a.rows - a.row0; q += kWarps * G) {
-    // this chunk's wavelength-integral partials: partials[b][row0 + q][L][4]
-    double* part = a.partials + ((int64_t)b * a.rows + a.row0 + q) * L * 4;
+    // staged table elements: a private [4 S][32][V] block per warp (the warps of a CTA may run
+    // chunks of different widths at the same time), sized for V = 2
+    const TabT* slot = reinterpret_cast<const TabT*>(sm_rows) + (size_t)(tid >> 5) * (4 * SS * 64) + lane * V;
+    const uint32_t stage = smem_u32(slot);
     // ---- per-wavelength constants ----
-    const int64_t j_raw = a.j0 + ((int64_t)q * 32 + lane) * V;
-    if (a.j0 + (int64_t)q * 32 * V >= a.j1) {    // padding row of the partials layout
-        for (int e = lane; e < L * 4; e += 32) part[e] = 0.0;
-        continue;
-    }
-    const bool live = j_raw < a.j1;              // (j1 - j0) % V == 0, so all V lanes are in range
-    const int64_t j = live ? j_raw : a.j1 - V;
+    const int64_t j_raw = jbase + (int64_t)lane * V;
+    const bool live = j_raw < n_lam;             // V == 2 only for even n_lam, so all V lanes are in range
+    const int64_t j = live ? j_raw : n_lam - V;
     const TabT* tabj = static_cast<const TabT*>(a.tab) + j;
     double* Fu = static_cast<double*>(a.F_up) + (int64_t)b * L * n_lam + j;
     double* Fd = static_cast<double*>(a.F_down) + (int64_t)b * L * n_lam + j;
@@ -833,15 +763,7 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
         Vec<V>::st(dt_out, one);
     }
 
-    double F2u[V], F1d[V], dtau[V], red[4], redp[4] = {0.0, 0.0, 0.0, 0.0}, oth[V], nxt[V], k[V];
-    // Two loop-structure options (compile-time, measured on B200 — DESIGN.md 3.1):
-    //  kFluxAsync: the stale stream of the NEXT layer is copied global -> shared with cp.async (two
-    //     thread-private slots used alternately) instead of being prefetched into registers;
-    //  kDeferRed: the warp reduction of a layer's four integrals is issued one iteration late so
-    //     its shuffle chain can overlap the fp64 chain of the next layer; the rows a sweep does not
-    //     visit (emit: level 0, absorb: level L-1) then receive the zeros redp starts with.
-    constexpr bool kFluxAsync = SWEEP_FLUX_ASYNC, kDeferRed = SWEEP_DEFER_RED;
-    uint32_t fcur = fstage, fnxt = fstage + (uint32_t)(kThreads * V * sizeof(double));
+    double F2u[V], F1d[V], dtau[V], red[4], oth[V], nxt[V], k[V];
     auto publish = [&](const double* r, int row) {
         const double r4 = warp_reduce4(r[0], r[1], r[2], r[3], lane);
         if ((lane & 7) == 0) part[row * 4 + (lane >> 3)] = r4;
@@ -851,7 +773,7 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
         const double* rec = sm_rec + rec8;
         const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
         if (L > 2) {
-            if (kFluxAsync) cp_async<V * 8>(fcur, pFd); else Vec<V>::ld(pFd, nxt);
+            Vec<V>::ld(pFd, nxt);
         }
         stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
         Vec<V>::ld(Fu + n_lam, t.Fcar);                                  // fluxes_up[1], stale
@@ -864,35 +786,21 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = 1; i < L - 1; ++i) {
-            if (kFluxAsync) lds_vec<V>(fcur, oth);                       // fluxes_down[i + 1]
-            else {
 #pragma unroll
-                for (int v = 0; v < V; ++v) oth[v] = nxt[v];
-            }
+            for (int v = 0; v < V; ++v) oth[v] = nxt[v];                 // fluxes_down[i + 1]
             pFd += n_lam;
-            if (i + 1 < L - 1) {                                         // one layer ahead
-                if (kFluxAsync) cp_async<V * 8>(fnxt, pFd); else Vec<V>::ld(pFd, nxt);
-            }
+            if (i + 1 < L - 1) Vec<V>::ld(pFd, nxt);                     // one layer ahead
             if (!(reinterpret_cast<const int64_t*>(rec + rec8)[2 + 5 * SS] & 1))  // level i + 1: new cell
                 stage_rows<TabT, S_T, V>(tabj, rec + rec8, S, n_lam, rowT, stage);
-            else if (kFluxAsync)
-                cp_async_commit();
-            if (kDeferRed) publish(redp, i - 1);
             layer_step<FREI_EMIT, V, false>(t, k, rec[0], oth, rec[rec8 + 1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :392-394
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
             }
-            if (kDeferRed) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) redp[c] = red[c];
-            } else {
-                publish(red, i);
-            }
+            publish(red, i);
             pFu_out += n_lam; pFd_out += n_lam; rec += rec8;
             if (DTAUS) pdt += n_lam;
-            { const uint32_t x = fcur; fcur = fnxt; fnxt = x; }
             cp_async_wait_all();
             gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         }
@@ -900,7 +808,6 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
             Vec<V>::ldg(a.f_toa + j, oth);                               // :379-382
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] *= fscale;
-            if (kDeferRed) publish(redp, L - 2);
             layer_step<FREI_EMIT, V, true>(t, k, rec[0], oth, 0.0, tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFd_out, F1d);
@@ -908,11 +815,11 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
             }
             publish(red, L - 1);
         }
-        if (!kDeferRed && lane < 4) part[lane] = 0.0;                    // level 0 is not visited
+        if (lane < 4) part[lane] = 0.0;                    // level 0 is not visited
     } else {
         const double* rec = sm_rec + (size_t)(L - 2) * rec8;
         const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
-        if (kFluxAsync) cp_async<V * 8>(fcur, pFu); else Vec<V>::ld(pFu, nxt);
+        Vec<V>::ld(pFu, nxt);
         stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
         Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, t.Fcar);               // fluxes_down[L-1]
         const double invTt = rec[rec8 + 1];
@@ -924,45 +831,94 @@ __global__ void __launch_bounds__(kThreads, (V == 1) ? SWEEP_MINB_V1 : (V == 4) 
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         for (int i = L - 2; i >= 0; --i) {
-            if (kFluxAsync) lds_vec<V>(fcur, oth);                       // fluxes_up[i], :512
-            else {
 #pragma unroll
-                for (int v = 0; v < V; ++v) oth[v] = nxt[v];
-            }
+            for (int v = 0; v < V; ++v) oth[v] = nxt[v];                 // fluxes_up[i], :512
             pFu -= n_lam;
-            if (i > 0) {                                                 // one layer ahead
-                if (kFluxAsync) cp_async<V * 8>(fnxt, pFu); else Vec<V>::ld(pFu, nxt);
-            }
+            if (i > 0) Vec<V>::ld(pFu, nxt);                             // one layer ahead
             if (i > 0 && !(reinterpret_cast<const int64_t*>(rec)[2 + 5 * SS] & 1))   // level i - 1: new cell
                 stage_rows<TabT, S_T, V>(tabj, rec - rec8, S, n_lam, rowT, stage);
-            else if (kFluxAsync)
-                cp_async_commit();
-            if (kDeferRed) publish(redp, i + 1);
             layer_step<FREI_ABSORB, V, false>(t, k, rec[0], oth, rec[1], tab, F2u, F1d, dtau, red);
             if (live) {
                 Vec<V>::st(pFu_out, F2u);                                // :521-522
                 Vec<V>::st(pFd_out, F1d);
                 if (DTAUS) Vec<V>::st(pdt, dtau);
             }
-            if (kDeferRed) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) redp[c] = red[c];
-            } else {
-                publish(red, i);
-            }
+            publish(red, i);
             pFu_out -= n_lam; pFd_out -= n_lam;
             if (DTAUS) pdt += n_lam;
-            { const uint32_t x = fcur; fcur = fnxt; fnxt = x; }
             if (i > 0) {
                 rec -= rec8;
                 cp_async_wait_all();
                 gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
             }
         }
-        if (kDeferRed) publish(redp, 0);
-        else if (lane < 4) part[(L - 1) * 4 + lane] = 0.0;               // level L-1 is not visited
+        if (lane < 4) part[(L - 1) * 4 + lane] = 0.0;               // level L-1 is not visited
     }
-  }
+}
+
+// The sweep kernel.  The wavelength axis is cut into a.n2 chunks of 64 wavelengths (two per thread)
+// followed by a.rows - a.n2 chunks of 32 (one per thread); chunk q owns row q of the partials.  For
+// a single atmosphere the grid holds at most one resident wave of CTAs (host: occupancy x SM
+// count) and warp w of CTA c takes the chunks q = w G + c, + kWarps G, ... (G = gridDim.x), so
+// every round of chunks is spread evenly over the SMs.  A chunk is a serial recurrence over the
+// layers: a launch proceeds in rounds of (resident warps) chunks and a partly filled last round
+// costs a whole chunk latency.  The host plan (sweep_plan) therefore fills the complete rounds with
+// 64-wide chunks and cuts what is left into 32-wide ones — twice as many warps, each with half the
+// instructions per layer — which shortens the tail of the launch (C2: 1.32 rounds of 64-wide chunks
+// cost 1.59 round times, one round + a 64 % full round of 32-wide chunks 1.38).
+// The level records are staged into shared memory by one TMA bulk copy per CTA.
+template <typename TabT, int S_T, int DIR, bool DTAUS>
+__global__ void __launch_bounds__(kThreads, (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB)
+sweep_kernel(SweepArgs a) {
+    extern __shared__ __align__(16) double smem[];
+    __shared__ __align__(8) uint64_t bar;
+    __shared__ double tab[32];                   // 2^(j/32) for exp_neg
+    const int tid = threadIdx.x, warp = tid >> 5;
+    const int b = blockIdx.y;
+    pdl_wait();                                  // records, T, active flags come from the previous kernel
+    if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: post_kernel may queue up behind it
+    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by post_kernel
+    if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
+    const int L = a.L, rec8 = a.lp.rec8;
+    if (tid < 32) tab[tid] = kExp2Tab[tid];
+    double* sm_rec = smem;                       // [L][rec8]
+    const void* sm_rows = smem + (size_t)L * rec8;
+
+    // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
+    const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const double* src = a.lp.rec + (int64_t)b * L * rec8;
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;"
+                     ::"r"(smem_u32(&bar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
+    }
+    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
+    const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
+    {   // ---- wait for the records ----
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile("{\n\t.reg .pred p;\n\t"
+                         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                         "selp.u32 %0, 1, 0, p;\n\t}"
+                         : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
+        }
+    }
+
+    const int G = gridDim.x;
+    for (int q = warp * G + blockIdx.x; q < a.rows; q += kWarps * G) {
+        double* part = a.partials + ((int64_t)b * a.rows + q) * L * 4;
+        if (q < a.n2)
+            sweep_chunk<TabT, S_T, DIR, 2, DTAUS>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale, fscale);
+        else
+            sweep_chunk<TabT, S_T, DIR, 1, DTAUS>(a, b, (int64_t)a.n2 * 64 + (int64_t)(q - a.n2) * 32, part,
+                                                  sm_rec, sm_rows, tab, sscale, fscale);
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1109,7 +1065,8 @@ struct PostArgs {
     int* p2p_error;
     unsigned long long epoch;
     int rank, world, B;
-    int rows, rows_per_chunk, nchunks;
+    const int32_t* plan_hdr;             // [0] = partial rows written by the sweep before this launch
+    int nchunks;
     int do_update, do_prep;
     int axes_smem;                       // the axes of K0 are searched in shared memory
     int stage_levels;                    // T, P, mmr (and the row offsets) of the atmosphere are staged in shared memory
@@ -1185,8 +1142,10 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
     pdl_wait();                                  // partials come from the sweep before
     pdl_launch_dependents();                     // the next sweep's CTAs may line up behind the serial tail
     if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
-    const int r0 = chunk * q.rows_per_chunk, r1 = min(q.rows, r0 + q.rows_per_chunk);
-    const double* p = q.partials + ((int64_t)b * q.rows + r0) * n;
+    const int rows = q.plan_hdr[0];
+    const int rows_per_chunk = (rows + q.nchunks - 1) / q.nchunks;
+    const int r0 = min(rows, chunk * rows_per_chunk), r1 = min(rows, r0 + rows_per_chunk);
+    const double* p = q.partials + ((int64_t)b * rows + r0) * n;
     const double s1 = cta_column_sum(p, r1 - r0, n, sm_post, G);
     if (threadIdx.x < n) q.chunk_sums[((int64_t)b * q.nchunks + chunk) * n + threadIdx.x] = s1;
     __threadfence();
@@ -1251,102 +1210,108 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
 // host side of the ABI
 // ---------------------------------------------------------------------------
 // ---- launch plan -------------------------------------------------------------------------------
-// The wavelength axis is cut into warp-chunks of 32 * V wavelengths (V = 2; V = 1 for odd
-// wavelength counts); the partials have one [L][4] row per chunk, padded to whole CTAs (the fp32
-// kernel shares the layout).  For a single atmosphere the grid is capped at one resident wave of
-// CTAs (occupancy x SMs) and the kernel strides over the chunks, which balances a partly filled
-// last round over the SMs: every column is a serial recurrence over the layers, so with the
-// hardware's dynamic CTA placement the SMs that drained first took whole extra CTAs while the
-// others idled (C2: 1.32 waves cost 1.7x one wave).  Batches keep one CTA per kWarps chunks:
-// converged atmospheres exit at once and must not strand the work of the others.
-static int g_num_sms = 0;
+// The wavelength axis is cut into n2 warp-chunks of 64 wavelengths (two per thread) followed by n1
+// chunks of 32 (one per thread); the partials have one [L][4] row per chunk, and the sweep kernel
+// leaves the row count in the workspace header for the reduction that follows it.  For a single
+// atmosphere the grid is capped at one resident wave of CTAs (occupancy x SMs) and the kernel
+// strides over the chunks, which balances every round over the SMs: a column is a serial recurrence
+// over the layers, so with the hardware's dynamic CTA placement the SMs that drained first took
+// whole extra CTAs while the others idled (C2: 1.32 waves cost 1.7x one wave).  Complete rounds
+// run 64-wide chunks; a last round that is at most half full is cut into 32-wide chunks (see
+// sweep_kernel).  Batches keep one CTA per kWarps chunks: converged atmospheres exit at once and
+// must not strand the work of the others.
+constexpr int kMaxDevices = 64;
 static int num_sms() {
-    if (g_num_sms == 0) {
-        int dev = 0, n = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess &&
-            cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-            g_num_sms = n;
-        else
-            g_num_sms = 148;
+    static int cache[kMaxDevices] = {0};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= kMaxDevices) return 148;
+    if (cache[dev] == 0) {
+        int n = 0;
+        cache[dev] = (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0) ? n : 148;
     }
-    return g_num_sms;
+    return cache[dev];
 }
 
-#ifndef SWEEP_V4
-#define SWEEP_V4 0                // experiment knob: 4 wavelengths per thread (2 CTAs/SM) when n_lam % 4 == 0
-#endif
-// Wavelengths per thread.  V = 1 for odd counts, and for problems so small that V = 2 would leave
-// SMs without a warp (fewer than two chunks of 64 per SM over the whole batch, e.g. C1's 5k bins =
-// 79 chunks on 148 SMs): a chunk is a serial recurrence, so halving it is the only parallelism left.
-static int g_force_V = 0;          // test hook (frei_b200_debug_plan): 0 = automatic
-static inline int sweep_V(int64_t n_lam, int B) {
-    if (n_lam % 2 != 0 || g_force_V == 1) return 1;
-    if (g_force_V != 2 && (int64_t)B * ((n_lam + 63) / 64) < SWEEP_V1_CHUNKS_PER_SM * (int64_t)num_sms()) return 1;
-    if (SWEEP_V4 && n_lam % 4 == 0) return 4;
-    return 2;
-}
-static inline int sweep_rows(int64_t n_lam, int B) {
-    const int64_t per_cta = (int64_t)kThreads * sweep_V(n_lam, B);
-    return (int)((n_lam + per_cta - 1) / per_cta) * kWarps;
+// test hook (frei_b200_debug_plan): 0 = automatic, 1 = 32-wide chunks only, 2 = 64-wide chunks only,
+// 3 = half of the 64-wide chunks replaced by 32-wide ones (exercises the mixed kernel at test sizes)
+static int g_force_V = 0;
+
+struct SweepPlan { int n2, n1; };
+// slots = warps of one resident wave (0 = not capped: batches)
+static SweepPlan sweep_plan(int64_t n_lam, int B, int64_t slots) {
+    SweepPlan p;
+    const int64_t c1 = (n_lam + 31) / 32, c2 = (n_lam + 63) / 64;
+    if (n_lam % 2 != 0 || g_force_V == 1) { p.n2 = 0; p.n1 = (int)c1; return p; }
+    if (g_force_V == 3) { p.n2 = (int)(c2 / 2); p.n1 = (int)((n_lam - 64 * (int64_t)p.n2 + 31) / 32); return p; }
+    p.n2 = (int)c2; p.n1 = 0;
+    if (g_force_V == 2) return p;
+    // so small that 64-wide chunks would leave SMs without a warp (C1's 5k bins = 79 chunks on 148
+    // SMs): a chunk is a serial recurrence, so halving it is the only parallelism left
+    if ((int64_t)B * c2 < SWEEP_V1_CHUNKS_PER_SM * (int64_t)num_sms()) { p.n2 = 0; p.n1 = (int)c1; return p; }
+    if (B > 1 || slots <= 0 || !SWEEP_MIXED_TAIL) return p;
+    const int64_t full = n_lam / (64 * slots);            // complete rounds of 64-wide chunks
+    const int64_t rem = n_lam - full * 64 * slots;        // wavelengths left for the last round
+    if (full >= 1 && rem > 0 && rem <= 32 * slots) {
+        p.n2 = (int)(full * slots);
+        p.n1 = (int)((rem + 31) / 32);
+    }
+    return p;
 }
 
 #ifndef SWEEP_PERSISTENT
 #define SWEEP_PERSISTENT 1        // experiment knob: 0 = one CTA per kWarps chunks for every launch
 #endif
 
-template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
-static int launch_sweep_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
-    static int resident = -1;     // CTAs per SM of this instantiation at the largest shared-memory size seen
-    static size_t smem_set = 0;
-    auto kern = sweep_kernel<TabT, S_T, DIR, V, DTAUS>;
-    if (resident < 0 || smem > smem_set) {
+template <typename TabT, int S_T, int DIR, bool DTAUS>
+static int launch_sweep_one(SweepArgs a, size_t smem, cudaStream_t st) {
+    // per device: CTAs per SM of this instantiation at the largest shared-memory size seen
+    static int resident[kMaxDevices];
+    static size_t smem_set[kMaxDevices];
+    static bool init = false;
+    if (!init) { for (int d = 0; d < kMaxDevices; ++d) { resident[d] = -1; smem_set[d] = 0; } init = true; }
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= kMaxDevices) return set_err(FREI_E_UNSUPPORTED, "device ordinal out of range%s%s");
+    auto kern = sweep_kernel<TabT, S_T, DIR, DTAUS>;
+    if (resident[dev] < 0 || smem > smem_set[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       (int)cudaSharedmemCarveoutMaxShared));
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
-        resident = nb > 0 ? nb : 1;
-        smem_set = smem;
+        resident[dev] = nb > 0 ? nb : 1;
+        smem_set[dev] = smem;
     }
     // One resident wave for a single atmosphere, with as many CTAs per SM as fit: launching fewer
     // to trade a nearly empty last round for fuller ones was measured (2, 3, 4 CTAs/SM at 100k ...
     // 600k wavelengths, scripts/ctas_scan.sh) and never won — 4 CTAs/SM are 0 ... 18 % faster than 3.
-    unsigned blocks = (unsigned)((a.rows - a.row0) / kWarps);
-    if (SWEEP_PERSISTENT && a.B == 1) {
-        const unsigned cap = (unsigned)(resident * num_sms());
-        if (blocks > cap) blocks = cap;
-    }
+    const bool persistent = SWEEP_PERSISTENT && a.B == 1;
+    const int64_t cap = (int64_t)resident[dev] * num_sms();
+    const SweepPlan p = sweep_plan(a.n_lam, a.B, persistent ? cap * kWarps : 0);
+    a.n2 = p.n2;
+    a.rows = p.n2 + p.n1;
+    unsigned blocks = (unsigned)((a.rows + kWarps - 1) / kWarps);
+    if (persistent && blocks > cap) blocks = (unsigned)cap;
     CUDA_TRY(launch_pdl(kern, dim3(blocks, a.B), dim3(kThreads), smem, st, a));
     return FREI_OK;
 }
 
-template <typename TabT, int S_T, int DIR>
-static int launch_sweep_v(const SweepArgs& a, int V, size_t smem, cudaStream_t st) {
-#if SWEEP_V4
-    if (V == 4)
-        return a.dtaus ? launch_sweep_one<TabT, S_T, DIR, 4, true>(a, smem, st)
-                       : launch_sweep_one<TabT, S_T, DIR, 4, false>(a, smem, st);
-#endif
-    if (a.dtaus)
-        return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, true>(a, smem, st)
-                      : launch_sweep_one<TabT, S_T, DIR, 1, true>(a, smem, st);
-    return V == 2 ? launch_sweep_one<TabT, S_T, DIR, 2, false>(a, smem, st)
-                  : launch_sweep_one<TabT, S_T, DIR, 1, false>(a, smem, st);
-}
-
 template <typename TabT, int S_T>
-static int launch_sweep_dir(const SweepArgs& a, int direction, int V, size_t smem, cudaStream_t st) {
-    if (direction == FREI_EMIT) return launch_sweep_v<TabT, S_T, FREI_EMIT>(a, V, smem, st);
-    return launch_sweep_v<TabT, S_T, FREI_ABSORB>(a, V, smem, st);
+static int launch_sweep_dir(const SweepArgs& a, int direction, size_t smem, cudaStream_t st) {
+    if (direction == FREI_EMIT)
+        return a.dtaus ? launch_sweep_one<TabT, S_T, FREI_EMIT, true>(a, smem, st)
+                       : launch_sweep_one<TabT, S_T, FREI_EMIT, false>(a, smem, st);
+    return a.dtaus ? launch_sweep_one<TabT, S_T, FREI_ABSORB, true>(a, smem, st)
+                   : launch_sweep_one<TabT, S_T, FREI_ABSORB, false>(a, smem, st);
 }
 
 template <typename TabT>
-static int launch_sweep(const SweepArgs& a, int direction, int V, size_t smem, cudaStream_t st) {
+static int launch_sweep(const SweepArgs& a, int direction, size_t smem, cudaStream_t st) {
     switch (a.S) {
-        case 1: return launch_sweep_dir<TabT, 1>(a, direction, V, smem, st);
-        case 3: return launch_sweep_dir<TabT, 3>(a, direction, V, smem, st);
-        case 8: return launch_sweep_dir<TabT, 8>(a, direction, V, smem, st);
-        default: return launch_sweep_dir<TabT, 0>(a, direction, V, smem, st);
+        case 1: return launch_sweep_dir<TabT, 1>(a, direction, smem, st);
+        case 3: return launch_sweep_dir<TabT, 3>(a, direction, smem, st);
+        case 8: return launch_sweep_dir<TabT, 8>(a, direction, smem, st);
+        default: return launch_sweep_dir<TabT, 0>(a, direction, smem, st);
     }
 }
 
@@ -1366,7 +1331,7 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
     ARG_TRY(B > 0 && L >= 3 && S > 0 && S <= kMaxS && n_lam > 0);
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
     if (partials)       // per-warp rows + chunk sums + per-atmosphere tickets
-        *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4);
+        *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4) + 16;
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -1398,7 +1363,7 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
 }
 
 int frei_b200_debug_plan(int32_t force_V) {
-    ARG_TRY(force_V == 0 || force_V == 1 || force_V == 2);
+    ARG_TRY(force_V >= 0 && force_V <= 3);
     g_force_V = force_V;
     return FREI_OK;
 }
@@ -1477,21 +1442,22 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.F_up = flux->F_up; a.F_down = flux->F_down; a.dtaus = flux->dtaus;
     a.partials = ws->partials;
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
-    a.rows = sweep_rows(tab->n_lam, atm->B);
-    a.j0 = 0; a.j1 = tab->n_lam; a.row0 = 0;
-    const int V = sweep_V(tab->n_lam, atm->B);
-    if (flux->dtype == FREI_F32)                 // fp32 arithmetic: sweep_f32.cu, same partials layout
-        return frei_launch_sweep_f32(a, tab->dtype, direction, V, (cudaStream_t)stream);
+    a.rows = 0; a.n2 = 0;                          // set by the launcher from its plan
+    a.plan_hdr = ws_plan_hdr(ws, atm->B, atm->L, tab->n_lam);
+    if (flux->dtype == FREI_F32) {               // fp32 arithmetic: sweep_f32.cu, same partials layout
+        const SweepPlan p = sweep_plan(tab->n_lam, atm->B, 0);
+        return frei_launch_sweep_f32(a, tab->dtype, direction, p.n2 > 0 ? 2 : 1, (cudaStream_t)stream);
+    }
 #ifndef SWEEP_SMEM_PAD
 #define SWEEP_SMEM_PAD 0          // experiment knob: extra dynamic shared memory to cap CTAs/SM
 #endif
+    // level records + thread-private slots for 4 S table elements of two wavelengths
     const size_t smem = (size_t)atm->L * a.lp.rec8 * sizeof(double) + SWEEP_SMEM_PAD +
-                        (size_t)4 * tab->S * kThreads * V * (tab->dtype == FREI_F32 ? 4 : 8) +
-                        (SWEEP_FLUX_ASYNC ? (size_t)2 * kThreads * V * sizeof(double) : 0);   // stale-stream slots
+                        (size_t)4 * tab->S * kThreads * 2 * (tab->dtype == FREI_F32 ? 4 : 8);
     if (smem > 200 * 1024)
         return set_err(FREI_E_UNSUPPORTED, "L * (species + layers) state exceeds shared memory%s%s");
-    return (tab->dtype == FREI_F32) ? launch_sweep<float>(a, direction, V, smem, (cudaStream_t)stream)
-                                    : launch_sweep<double>(a, direction, V, smem, (cudaStream_t)stream);
+    return (tab->dtype == FREI_F32) ? launch_sweep<float>(a, direction, smem, (cudaStream_t)stream)
+                                    : launch_sweep<double>(a, direction, smem, (cudaStream_t)stream);
 }
 
 static void fill_prep(PrepArgs& a, const frei_table* tab, const frei_atmosphere* atm,
@@ -1527,18 +1493,19 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     ARG_TRY(atm && ws && ws->partials && ws->sums && n_lam > 0);
     ARG_TRY(atm->L >= 3 && atm->L <= 256 && atm->B <= 65535);
     PostArgs q;
-    q.rows = sweep_rows(n_lam, atm->B);
-    // Two reduction stages of about sqrt(rows) rows each keep the dependent load batches of both
-    // short (C1: 9 chunks, C2: 56, C3 on one GPU: 125); at most kPostChunks, the workspace layout's bound.
-    q.nchunks = (int)ceil(sqrt((double)q.rows));
+    // The row count of the sweep's plan is read on the device from the workspace header; the grid
+    // only needs a bound.  Two reduction stages of about sqrt(rows) rows each keep the dependent
+    // load batches of both short (C1: 9 chunks, C2: 56, C3 on one GPU: 125); at most kPostChunks,
+    // the workspace layout's bound.
+    const int64_t rows_est = (n_lam + 63) / 64;
+    q.nchunks = (int)ceil(sqrt((double)rows_est));
     if (q.nchunks > kPostChunks) q.nchunks = kPostChunks;
     if (q.nchunks < 1) q.nchunks = 1;
-    q.rows_per_chunk = (q.rows + q.nchunks - 1) / q.nchunks;
-    q.nchunks = (q.rows + q.rows_per_chunk - 1) / q.rows_per_chunk;
     const int64_t n = (int64_t)atm->L * 4;
     q.partials = ws->partials;
-    q.chunk_sums = ws->partials + (int64_t)atm->B * sweep_rows_max(n_lam) * n;
-    q.counters = reinterpret_cast<unsigned int*>(q.chunk_sums + (int64_t)atm->B * kPostChunks * n);
+    q.chunk_sums = ws_chunk_sums(ws, atm->B, atm->L, n_lam);
+    q.counters = ws_counters(ws, atm->B, atm->L, n_lam);
+    q.plan_hdr = ws_plan_hdr(ws, atm->B, atm->L, n_lam);
     q.sums = ws->sums;
     q.active = atm->active;
     q.peer_bufs = nullptr; q.peer_flags = nullptr; q.p2p_error = nullptr;

@@ -177,12 +177,13 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
     constexpr int RW = 4 / (THREADS / 32);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
+    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by post_kernel
     if (a.active && !a.active[b]) return;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
     double* sm_rec = smem;
     const TabT* slot = reinterpret_cast<const TabT*>(smem + (size_t)L * rec8) + tid * V;
     const uint32_t stage = smem_u32(slot);
-    double* part = a.partials + ((int64_t)b * a.rows + a.row0 + blockIdx.x * 4 + warp * RW) * L * 4;
+    double* part = a.partials + ((int64_t)b * a.rows + blockIdx.x * 4 + warp * RW) * L * 4;
     const int64_t n_lam = a.n_lam;
 
     const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
@@ -199,9 +200,9 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
                      ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
     }
 
-    const int64_t j_raw = a.j0 + ((int64_t)blockIdx.x * THREADS + tid) * V;
-    const bool live = j_raw < a.j1;
-    const int64_t j = live ? j_raw : a.j1 - V;
+    const int64_t j_raw = ((int64_t)blockIdx.x * THREADS + tid) * V;
+    const bool live = j_raw < n_lam;
+    const int64_t j = live ? j_raw : n_lam - V;
     const TabT* tabj = static_cast<const TabT*>(a.tab) + j;
     const int64_t rowT = (int64_t)a.N_T * n_lam;
     float* Fu = static_cast<float*>(a.F_up) + (int64_t)b * L * n_lam + j;
@@ -331,8 +332,10 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
 }
 
 template <typename TabT, int DIR, int V, int THREADS, bool DTAUS>
-int launch_one(const SweepArgs& a, size_t smem, cudaStream_t st) {
-    const unsigned blocks = (unsigned)((a.j1 - a.j0 + (int64_t)THREADS * V - 1) / ((int64_t)THREADS * V));
+int launch_one(SweepArgs a, size_t smem, cudaStream_t st) {
+    const unsigned blocks = (unsigned)((a.n_lam + (int64_t)THREADS * V - 1) / ((int64_t)THREADS * V));
+    a.rows = (int)blocks * 4;                    // a CTA fills four rows of the partials
+    a.n2 = 0;
     if (cudaFuncSetAttribute(sweep_f32_kernel<TabT, DIR, V, THREADS, DTAUS>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
         cudaFuncSetAttribute(sweep_f32_kernel<TabT, DIR, V, THREADS, DTAUS>,
@@ -356,10 +359,9 @@ int launch_v(const SweepArgs& a, int direction, cudaStream_t st) {
 
 }  // namespace
 
-// The launch covers [a.j0, a.j1) with the CTA size (in wavelengths) of the fp64 plan (plan_V =
-// its wavelengths per thread): 256 when plan_V >= 2 (V = 4 x 64 threads, or V = 2 x 128 threads),
+// CTA size in wavelengths: 256 when plan_V >= 2 (V = 4 x 64 threads, or V = 2 x 128 threads),
 // else 128 (V = 1: odd counts and very small problems).
-int frei_launch_sweep_f32(const SweepArgs& a, int table_dtype, int direction, int plan_V, cudaStream_t st) {
+int frei_launch_sweep_f32(SweepArgs a, int table_dtype, int direction, int plan_V, cudaStream_t st) {
     const int64_t n = a.n_lam;
     if (table_dtype == FREI_F32) {
         if (plan_V == 1) return launch_v<float, 1, 128>(a, direction, st);

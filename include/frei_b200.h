@@ -153,10 +153,14 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
  * exp(-x), 1 - exp(-x) as computed by the kernels' branch-free fp64 routines. */
 int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream);
 
-/* Test hook: wavelengths per thread of the sweep plan.  0 (default) = automatic: 2, or 1 for odd
- * wavelength counts and for problems too small to give every SM two warps; 1 / 2 force the
- * choice (2 only takes effect for even counts).  Process-wide; not meant for production use:
- * it exists so that small parity cases can exercise the two-per-thread kernels. */
+/* Test hook: shape of the sweep plan.  The sweep cuts the wavelength axis into warp-chunks of 64
+ * wavelengths (two per thread) followed by chunks of 32 (one per thread).  0 (default) = automatic:
+ * complete rounds of resident warps take 64-wide chunks and a last round that is at most half full
+ * is cut into 32-wide ones; 32-wide only for odd wavelength counts and for problems too small to
+ * give every SM two warps.  1 / 2 force 32-wide / 64-wide chunks only, 3 forces a mixed plan (half
+ * of the 64-wide chunks, the rest 32-wide); 2 and 3 only take effect for even counts.
+ * Process-wide; not meant for production use: it exists so that small parity cases can exercise
+ * every chunk shape of the production-size kernels. */
 int frei_b200_debug_plan(int32_t force_V);
 
 /* K0.  Bracket (P_i, T_i) of every level in every species' axes with the rule

@@ -14,7 +14,10 @@ ap.add_argument('--config', default='C2')
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--table-dtype', type=int, default=64)
 ap.add_argument('--nlam', type=int, default=0)
+ap.add_argument('--plan', type=int, default=0)
 a = ap.parse_args()
+from frei_b200 import _cabi  # noqa: E402
+_cabi.check(_cabi.load().frei_b200_debug_plan(a.plan))
 L, n_lam, S, T_ref = synthetic.CONFIGS[a.config]
 if a.nlam:
     n_lam = a.nlam

@@ -15,7 +15,10 @@ ap.add_argument('--S', type=int, default=3)
 ap.add_argument('--table-dtype', type=int, default=64)
 ap.add_argument('--flux-dtype', type=int, default=64)
 ap.add_argument('--nlam', type=int, nargs='+', default=[50_000, 100_000, 151_552, 200_000, 303_104, 400_000, 800_000])
+ap.add_argument('--plan', type=int, default=0, help='frei_b200_debug_plan: 0 auto, 1 32-wide, 2 64-wide, 3 mixed')
 a = ap.parse_args()
+from frei_b200 import _cabi  # noqa: E402
+_cabi.check(_cabi.load().frei_b200_debug_plan(a.plan))
 dt = FREI_F32 if a.table_dtype == 32 else FREI_F64
 for n_lam in a.nlam:
     w = synthetic.make_workload(a.L, n_lam, a.S, 2400.0, table_f32=(dt == FREI_F32))

@@ -28,13 +28,15 @@ LD = np.longdouble
 TINY = 1e-250        # fluxes below this are denormal-range attenuated starlight
 
 
-@pytest.fixture(params=['auto', 'v2'])
+@pytest.fixture(params=['auto', 'v2', 'mixed'])
 def plan(request):
-    """Sweep plan: automatic (one wavelength per thread for these small cases) and forced
-    two-per-thread (what every production-size launch uses, partly filled last chunk included)."""
+    """Sweep plan: automatic (32-wide warp-chunks, one wavelength per thread, for these small
+    cases), forced 64-wide chunks (two per thread: the complete rounds of every production-size
+    launch, partly filled last chunk included) and forced mixed (64-wide chunks followed by 32-wide
+    ones: what a production-size launch with a short last round runs)."""
     from frei_b200 import _cabi
     lib = _cabi.load()
-    _cabi.check(lib.frei_b200_debug_plan(2 if request.param == 'v2' else 0))
+    _cabi.check(lib.frei_b200_debug_plan({'auto': 0, 'v2': 2, 'mixed': 3}[request.param]))
     yield request.param
     _cabi.check(lib.frei_b200_debug_plan(0))
 
