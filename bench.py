@@ -179,32 +179,67 @@ def run_reference(args):
 # ---------------------------------------------------------------------------
 # GPU arm
 # ---------------------------------------------------------------------------
-def run_ours(args):
+# fp64 thread-level instructions per evaluation of the sweep kernel, used when profiles/traffic.json
+# has no ncu entry for the workload (values of the committed C2 capture, S = 3)
+FALLBACK_OPS_PER_EVAL = {'dfma': 55.0, 'dmul': 33.1, 'dadd': 20.4}
+
+
+def read_fp64_ops(workload, table_dtype, flux_dtype, evals_per_launch_captured):
+    """fp64 thread instructions per evaluation from the committed ncu capture of this workload."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
+            e = json.load(fh)[f'{workload}_tab{table_dtype}_flux{flux_dtype}_n1']
+        ops = e['fp64_thread_ops_per_launch']
+        return {k: ops[k] / evals_per_launch_captured for k in ('dfma', 'dmul', 'dadd')}, e['source']
+    except (OSError, ValueError, KeyError):
+        return None, None
+
+
+def distinct_table_rows(w, S):
+    """
+    Number of distinct (species, P node, T node) table rows the levels of the initial profile
+    touch: the compulsory table traffic of one sweep is that many rows of n_lambda elements
+    (a row shared by neighbouring levels, or by neighbouring (P,T) cells, is read from HBM once
+    if it stays on chip).  Same bracket rule as K0 (scipy find_indices).
+    """
+    def idx(x, v):
+        i = np.searchsorted(x, v, side='right') - 1
+        return np.clip(i, 0, len(x) - 2)
+    ip, it = idx(w['axis_P'], w['P_bar']), idx(w['axis_T'], w['T_init'])
+    rows = set()
+    for a, b in zip(ip.tolist(), it.tolist()):
+        rows.update([(a, b), (a, b + 1), (a + 1, b), (a + 1, b + 1)])
+    return S * len(rows)
+
+
+def setup_dist():
     import torch
     import torch.distributed as dist
-    from frei_b200 import synthetic
-    from frei_b200.core import Grid, Planet
-    from frei_b200.engine import Engine, FREI_EMIT, FREI_ABSORB, FREI_F32, FREI_F64, shard_range
-
     world = int(os.environ.get('WORLD_SIZE', '1'))
     rank = int(os.environ.get('RANK', '0'))
     local_rank = int(os.environ.get('LOCAL_RANK', '0'))
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
     group = None
-    if world > 1:
+    if world > 1 and not dist.is_initialized():
         dist.init_process_group('nccl', device_id=dev)
+    if world > 1:
         group = dist.group.WORLD
-    if args.gpus != world and rank == 0:
-        print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
+    return world, rank, local_rank, dev, group
 
-    L, n_lam_w, S, T_ref, scaling, wl_text = WORKLOADS[args.workload]
+
+def time_sweeps(args, workload, world, rank, dev, group, tdtype, fdtype, steps, warmup, sample_clocks=False,
+                local_rank=0):
+    """
+    One workload on this job's GPUs: W untimed + K timed RE iterations (emit + absorb), CUDA events,
+    max over ranks.  Returns a dict with everything the JSON line reports about it.
+    """
+    import torch
+    import torch.distributed as dist
+    from frei_b200 import synthetic
+    from frei_b200.engine import Engine, FREI_EMIT, FREI_ABSORB, FREI_F32, shard_range
+    L, n_lam_w, S, T_ref, scaling, wl_text = WORKLOADS[workload]
     n_lam_global = n_lam_w * world if scaling == 'weak' else n_lam_w   # weak: bins per GPU fixed
-    if args.flux_dtype == 32:
-        args.table_dtype = 32
-    tdtype = FREI_F32 if args.table_dtype == 32 else FREI_F64
-    fdtype = FREI_F32 if args.flux_dtype == 32 else FREI_F64
-    b_flux = 4 if fdtype == FREI_F32 else 8
     w = synthetic.make_workload(L, n_lam_global, S, T_ref, table_f32=(tdtype == FREI_F32))
     lo, hi = shard_range(n_lam_global, rank, world)
     table = synthetic.device_table(w, tdtype, lam_range=(lo, hi), device=dev)
@@ -222,11 +257,11 @@ def run_ours(args):
         eng.sweep(FREI_EMIT)
         eng.sweep(FREI_ABSORB)
 
-    for _ in range(args.warmup):
+    for _ in range(warmup):
         step()
     sync()
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if sample_clocks and rank == 0:
         sampler.start()
         time.sleep(0.25)
     # The sweep kernel is timed live inside the timed region with CUDA events on its stream, on
@@ -237,7 +272,7 @@ def run_ours(args):
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     sync()
     ev0.record()
-    for i in range(args.steps):
+    for i in range(steps):
         eng.sweep_events = events if i % 4 == 0 else None
         step()
     ev1.record()
@@ -245,49 +280,107 @@ def run_ours(args):
     ms = ev0.elapsed_time(ev1)
     sweep_ms = [a.elapsed_time(b) for a, b in events]
     eng.sweep_events = None
-    launches = eng.launches - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    eng.check_errors()
+    clocks = sampler.stop() if (sample_clocks and rank == 0) else None
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
     evals_per_step = 2 * (L - 1) * n_lam_global
-    value = evals_per_step * args.steps / (ms * 1e-3)
+    return dict(w=w, table=table, eng=eng, L=L, S=S, n_lam_global=n_lam_global, lo=lo, hi=hi,
+                scaling=scaling, text=wl_text, ms=ms, steps=steps, warmup=warmup,
+                value=evals_per_step * steps / (ms * 1e-3), sweep_avg_ms=float(np.mean(sweep_ms)),
+                sweeps_timed=len(sweep_ms), launches=eng.launches - launches0, clocks=clocks,
+                collective=('p2p-fused' if eng._p2p is not None else 'nccl') if world > 1 else None)
 
-    # roofline of the dominant kernel (the layer sweep), this rank's launches
+
+def fp64_peak(dev):
+    """Thread-level DFMA/s measured now on this GPU (frei_b200_fp64_peak)."""
+    import ctypes as C
+    import torch
+    from frei_b200 import _cabi
+    lib = _cabi.load()
+    n = 2048 * torch.cuda.get_device_properties(dev).multi_processor_count
+    scratch = torch.empty(n, dtype=torch.float64, device=dev)
+    out = C.c_double()
+    _cabi.check(lib.frei_b200_fp64_peak(scratch.data_ptr(), n, C.byref(out),
+                                        torch.cuda.current_stream(dev).cuda_stream))
+    return out.value
+
+
+def roofline_of(r, args, tdtype, fdtype, world, dev):
+    """Roofline of the sweep kernel of run `r` against the resource that binds it."""
+    from frei_b200.engine import FREI_F32
+    L, S, n_loc = r['L'], r['S'], r['hi'] - r['lo']
     b_tab = 4 if tdtype == FREI_F32 else 8
-    bytes_per_eval = 4 * S * b_tab + 3 * b_flux
-    sweep_avg_ms = float(np.mean(sweep_ms))
-    algo_bytes = (L - 1) * (hi - lo) * bytes_per_eval
-    peak, peak_src = read_peaks()
-    achieved = algo_bytes / (sweep_avg_ms * 1e-3) / 1e9
-    traffic, traffic_src = read_traffic(args.workload, args.table_dtype, args.flux_dtype, world)
-    # the pipe that actually limits the fp64 kernel: executed-path SASS counts of the
-    # layer loop for S = 3, two wavelengths per thread, E = 1 form (scripts/sass_loop_mix.py):
-    # 110 DFMA + 66 DMUL + 39 DADD per warp and layer = 64 evaluations
-    fp64_info = None
-    if S == 3 and fdtype == FREI_F64:
-        sm_hz = 1.965e9
-        evals_s = (L - 1) * (hi - lo) / (sweep_avg_ms * 1e-3)
-        inst_per_eval, flops_per_eval = 215 / 64, (2 * 110 + 66 + 39) / 2
-        # pipe cycles per warp instruction: 2, or 3 with three distinct register operands (60 of the
-        # 110 DFMAs; measured, scripts/fp64_operands.cu) -> 490 cycles per warp and layer
-        pipe_cycles_per_eval = (2 * 155 + 3 * 60) / 64
-        fp64_info = {'warp_inst_per_eval': inst_per_eval, 'flops_per_eval': flops_per_eval,
-                     'achieved_tflops': evals_s * flops_per_eval / 1e12,
-                     'peak_tflops_nominal': 148 * 64 * 2 * sm_hz / 1e12,
-                     'pipe_frac': evals_s * pipe_cycles_per_eval / (148 * 4 * sm_hz),
-                     'note': 'fp64 pipe occupancy implied by the kernel time: pipe cycles of the '
-                             'issued warp instructions / (148 SMs x 4 sub-partitions x 1.965 GHz); '
-                             'ncu sm__pipe_fp64_cycles_active: 42-46 % (capture r1i)'}
+    b_flux = 4 if fdtype == FREI_F32 else 8
+    t = r['sweep_avg_ms'] * 1e-3
+    evals = (L - 1) * n_loc
+    peak_hbm, peak_src = read_peaks()
+    algo_bytes = evals * (4 * S * b_tab + 3 * b_flux)                     # SURVEY 8d
+    reuse_bytes = evals * 3 * b_flux + distinct_table_rows(r['w'], S) * n_loc * b_tab
+    traffic, traffic_src = read_traffic(args.workload, args.table_dtype, args.flux_dtype, 1)
+    hbm = {'peak': peak_hbm, 'peak_source': peak_src, 'unit': 'GB/s',
+           'algorithmic_bytes': algo_bytes, 'algorithmic_gbs': algo_bytes / t / 1e9,
+           'reuse_aware_bytes': reuse_bytes, 'reuse_aware_gbs': reuse_bytes / t / 1e9,
+           'reuse_aware_frac': reuse_bytes / t / 1e9 / peak_hbm,
+           'traffic': traffic, 'traffic_source': traffic_src,
+           'traffic_gbs': (traffic / t / 1e9) if traffic else None,
+           'note': 'algorithmic = SURVEY 8d (4 S table rows + 3 flux words per evaluation, every level '
+                   're-reads its rows); reuse_aware = 3 flux words per evaluation + every DISTINCT table '
+                   'row the levels touch once (rows shared by the levels of a (P,T) cell stay on chip); '
+                   'traffic = dram__bytes_read + write of one launch (ncu --set full capture)'}
+    common = {'kernel': 'sweep_kernel', 'kernel_avg_ms': r['sweep_avg_ms'],
+              'kernel_launches_timed': r['sweeps_timed'], 'evals_per_launch': evals,
+              'kernel_share_of_step': 2 * r['sweep_avg_ms'] / (r['ms'] / r['steps']), 'hbm': hbm}
+    if fdtype == FREI_F32:
+        # fp32 arithmetic: the kernel streams; compulsory (reuse-aware) bytes against the copy bandwidth
+        return dict(common, bound='hbm', achieved=hbm['reuse_aware_gbs'], peak=peak_hbm, unit='GB/s',
+                    frac=hbm['reuse_aware_frac'], traffic=traffic,
+                    note='fp32 arithmetic: bound by HBM; achieved = reuse-aware compulsory bytes / kernel '
+                         'time (the SURVEY 8d algorithmic bytes would count table rows that never leave '
+                         'the chip: see hbm.algorithmic_gbs)')
+    # fp64 arithmetic: the fp64 pipe binds (ncu: 45 % pipe-active vs 42 % of HBM on real traffic)
+    ops, ops_src = read_fp64_ops(args.workload, args.table_dtype, args.flux_dtype,
+                                 (WORKLOADS[args.workload][0] - 1) * WORKLOADS[args.workload][1])
+    if ops is None:
+        ops, ops_src = FALLBACK_OPS_PER_EVAL, 'fallback: counts of the committed C2 capture (S = 3)'
+    dfma_peak = fp64_peak(dev)                                             # thread DFMA/s, measured now
+    flops_per_eval = 2 * ops['dfma'] + ops['dmul'] + ops['dadd']
+    slots_per_eval = ops['dfma'] + ops['dmul'] + ops['dadd']
+    achieved = flops_per_eval * evals / t / 1e12
+    peak = 2 * dfma_peak / 1e12
+    return dict(common, bound='fp64', achieved=achieved, peak=peak, unit='TFLOP/s', frac=achieved / peak,
+                traffic=traffic,
+                pipe_frac=slots_per_eval * evals / t / dfma_peak,
+                fp64={'thread_ops_per_eval': ops, 'ops_source': ops_src, 'flops_per_eval': flops_per_eval,
+                      'peak_dfma_per_s': dfma_peak,
+                      'peak_source': 'measured in this run: frei_b200_fp64_peak (register-operand DFMA '
+                                     'chains, 16 warps per scheduler, best of 3, CUDA events)'},
+                note='fp64 arithmetic: bound by the fp64 pipe.  achieved = executed fp64 flops per launch '
+                     '(ncu thread-level DFMA x 2 + DMUL + DADD of the committed capture, per evaluation) '
+                     '/ kernel time; peak = DFMA rate measured in this run x 2.  pipe_frac counts issue '
+                     'slots (a DMUL or DADD occupies the pipe as long as a DFMA).  The HBM view is under '
+                     '"hbm": real DRAM traffic is ~1/3 of the SURVEY 8d algorithmic bytes.')
 
-    # e2e through the public API: Grid.emission_spectrum with host buffers
-    e2e = None
+
+def run_e2e(args, r, world, rank, dev, group, fdtype):
+    """The same metric through the public API with host buffers: Grid.emission_spectrum."""
+    import torch
+    import torch.distributed as dist
+    from frei_b200.core import Grid, Planet
+    w, L, S = r['w'], r['L'], r['S']
+    pl = w['planet']
+
+    def sync():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
     try:
         planet = Planet(a_rstar=pl['a_rstar'], m_bar=pl['m_bar'], g=pl['g'] / 100.0,
                         T_star=pl['T_star'], alpha=pl['alpha'])
         grid = Grid(planet, lam=w['lam_um'], pressures=w['P_bar'], init_temperatures=w['T_init'])
-        grid.attach_device_table(table, species=w['species'])
+        grid.attach_device_table(r['table'], species=w['species'])
         grid.flux_dtype = fdtype
         k_e2e = max(2, args.steps)
         # N > 1: every rank keeps its own wavelength slice of the results (gather='local'), so the
@@ -305,86 +398,131 @@ def run_ours(args):
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dt = float(tt.item())
-        n_loc = hi - lo
-        h2d = (8 * n_lam_global + 8 * L * (2 + S) + 8 * 3) / k_e2e
-        d2h = 2 * L * 8 + 0.25 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e  # T history, flag polls, fp64 results
-        e2e = {'value': (2 * k_e2e + 1) * (L - 1) * n_lam_global / dt, 'unit': UNIT,
-               'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
-               'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}'
-                       + (", group=WORLD, gather='local'" if world > 1 else '') +
-                       ') incl. setup, device-side convergence rule polled every 4 iterations, '
-                       'final emit, T history + spectrum + dtaus D2H into pinned host arrays'
-                       + (' (each rank: its own wavelength slice)' if world > 1 else ''),
-               'seconds': dt}
+        n_loc = r['hi'] - r['lo']
+        # per solve: T, P, mmr, g, m_bar, alpha up (the wavelength grid and the opacity table are
+        # resident, as in the reference where they are loaded once per Grid); down: T history
+        # (2 L doubles per iteration), convergence flags, and once spectrum + dtaus + final T
+        h2d = (8 * L * (2 + S) + 8 * 3) / k_e2e
+        d2h = 2 * L * 8 + 0.25 + ((L + 1) * n_loc * 8 + L * 8) / k_e2e
+        return {'value': (2 * k_e2e + 1) * (L - 1) * r['n_lam_global'] / dt, 'unit': UNIT,
+                'h2d_bytes_per_step': int(h2d), 'd2h_bytes_per_step': int(d2h),
+                'call': f'Grid.emission_spectrum(n_timesteps={k_e2e}'
+                        + (", group=WORLD, gather='local'" if world > 1 else '') +
+                        ') incl. per-solve setup, device-side convergence rule, final emit, '
+                        'T history + spectrum + dtaus D2H into pinned host arrays'
+                        + (' (each rank: its own wavelength slice)' if world > 1 else '')
+                        + '; the opacity table upload is load-time (Grid.load_opacities) and outside',
+                'seconds': dt, 'frac_of_device_rate': None}
     except Exception as exc:                                   # pragma: no cover
-        e2e = {'value': None, 'error': repr(exc)}
+        return {'value': None, 'error': repr(exc)}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from frei_b200.engine import FREI_F32, FREI_F64
+
+    world, rank, local_rank, dev, group = setup_dist()
+    if args.gpus != world and rank == 0:
+        print(f'warning: --gpus {args.gpus} but WORLD_SIZE={world}', file=sys.stderr)
+    if args.flux_dtype == 32:
+        args.table_dtype = 32
+    tdtype = FREI_F32 if args.table_dtype == 32 else FREI_F64
+    fdtype = FREI_F32 if args.flux_dtype == 32 else FREI_F64
+    b_flux = 4 if fdtype == FREI_F32 else 8
+    b_tab = 4 if tdtype == FREI_F32 else 8
+
+    r = time_sweeps(args, args.workload, world, rank, dev, group, tdtype, fdtype, args.steps, args.warmup,
+                    sample_clocks=True, local_rank=local_rank)
+    L, S, lo, hi = r['L'], r['S'], r['lo'], r['hi']
+    roof = roofline_of(r, args, tdtype, fdtype, world, dev)
+    e2e = run_e2e(args, r, world, rank, dev, group, fdtype)
+    if e2e.get('value'):
+        e2e['frac_of_device_rate'] = e2e['value'] / r['value']
+    table_numel = r['table'].values.numel()
+    for k in ('eng', 'table', 'w'):
+        r[k] = None
+    torch.cuda.empty_cache()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == 'C2':
         cpu = cpu_baseline_one_core()
 
+    # secondary records: the other BASELINE.json configurations this job size is quoted on
+    extras = {}
+    if not args.no_extras and args.workload == 'C2' and args.flux_dtype == 64 and args.table_dtype == 64:
+        try:
+            c3 = time_sweeps(args, 'C3', world, rank, dev, group, FREI_F64, FREI_F64, steps=6, warmup=3)
+            extras['strong_c3'] = {
+                'metric': METRIC, 'value': c3['value'], 'unit': UNIT, 'scaling': 'strong',
+                'ms_per_step': c3['ms'] / c3['steps'], 'steps': c3['steps'], 'warmup': c3['warmup'],
+                'kernel_avg_ms': c3['sweep_avg_ms'], 'n_gpus': world, 'collective': c3['collective'],
+                'workload': WORKLOADS['C3'][5], 'n_layers': c3['L'], 'n_lambda_global': c3['n_lam_global'],
+                'n_species': c3['S'], 'dtype': 'f64'}
+            c3 = None
+            torch.cuda.empty_cache()
+        except Exception as exc:                               # pragma: no cover
+            extras['strong_c3'] = {'error': repr(exc)}
+        try:
+            f32 = time_sweeps(args, 'C2', world, rank, dev, group, FREI_F32, FREI_F32, steps=args.steps,
+                              warmup=3)
+            a32 = argparse.Namespace(**dict(vars(args), table_dtype=32, flux_dtype=32))
+            extras['fp32_c2'] = {
+                'metric': METRIC, 'value': f32['value'], 'unit': UNIT, 'scaling': f32['scaling'],
+                'ms_per_step': f32['ms'] / f32['steps'], 'dtype': 'f32', 'n_gpus': world,
+                'note': 'fp32 table, flux state and arithmetic, fp64 wavelength integrals (contract 1e-4)',
+                'roofline': roofline_of(f32, a32, FREI_F32, FREI_F32, world, dev)}
+            f32 = None
+            torch.cuda.empty_cache()
+        except Exception as exc:                               # pragma: no cover
+            extras['fp32_c2'] = {'error': repr(exc)}
+        try:
+            extras['c4'] = batch_solve(args, world, rank, dev)
+        except Exception as exc:                               # pragma: no cover
+            extras['c4'] = {'error': repr(exc)}
+
     if rank == 0:
         out = {
-            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
-            'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True,
-            'scaling': scaling, 'vs_baseline': None, 'dtype': f'f{args.flux_dtype}', 'data': 'synthetic',
+            'metric': METRIC, 'value': r['value'], 'unit': UNIT, 'n_gpus': world, 'steps': args.steps,
+            'warmup': args.warmup, 'ms_per_step': r['ms'] / args.steps, 'higher_is_better': True,
+            'scaling': r['scaling'], 'vs_baseline': None, 'dtype': f'f{args.flux_dtype}', 'data': 'synthetic',
             'config': {
-                'workload': wl_text,
-                'n_layers': L, 'n_lambda_global': n_lam_global, 'n_species': S,
+                'workload': r['text'],
+                'n_layers': L, 'n_lambda_global': r['n_lam_global'], 'n_species': S,
                 'table_dtype': f'f{args.table_dtype}', 'flux_dtype': f'f{args.flux_dtype}',
                 'parallelism': f'lambda-sharded x{world}' if world > 1 else 'single GPU',
-                'collective': ('p2p-fused' if eng._p2p is not None else 'nccl') if world > 1 else None,
+                'collective': r['collective'],
                 'l2': 'inputs larger than L2: flux state '
                       f'{2 * L * (hi - lo) * b_flux / 1e6:.0f} MB + table '
-                      f'{table.values.numel() * b_tab / 1e6:.0f} MB per GPU touched every step'
-                      if 2 * L * (hi - lo) * b_flux + table.values.numel() * b_tab > 130e6 else
+                      f'{table_numel * b_tab / 1e6:.0f} MB per GPU touched every step'
+                      if 2 * L * (hi - lo) * b_flux + table_numel * b_tab > 130e6 else
                       'working set fits L2 (flux state '
-                      f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB): 256 MB scratch written between steps '
-                      'outside the event pairs is NOT done; kernel times are warm-L2',
+                      f'{2 * L * (hi - lo) * 8 / 1e6:.0f} MB): kernel times are warm-L2',
             },
-            'roofline': {'bound': 'hbm', 'achieved': achieved, 'peak': peak, 'unit': 'GB/s',
-                         'frac': achieved / peak, 'traffic': traffic, 'peak_source': peak_src,
-                         'traffic_source': traffic_src,
-                         'dram_gbs': (traffic / (sweep_avg_ms * 1e-3) / 1e9) if traffic else None,
-                         'note': 'achieved = algorithmic bytes (SURVEY 8d: 4 S table rows + 3 flux '
-                                 'words per evaluation) / kernel time; table rows shared by the '
-                                 'levels of one (P,T) cell are served on chip, so the DRAM traffic '
-                                 '(traffic, dram_gbs) is lower and frac can exceed 1; the kernel '
-                                 'is bound by fp64 issue + shared-memory bandwidth (DESIGN.md 3.1)',
-                         'kernel': 'sweep_kernel', 'kernel_avg_ms': sweep_avg_ms,
-                         'kernel_launches_timed': len(sweep_ms),
-                         'bytes_per_eval': bytes_per_eval,
-                         'kernel_share_of_step': 2 * sweep_avg_ms / (ms / args.steps),
-                         'fp64': fp64_info},
+            'roofline': roof,
             'cpu_baseline': cpu,
             'e2e': e2e,
-            'gpu_launches': launches,
-            'clocks': clocks,
+            'gpu_launches': r['launches'],
+            'clocks': r['clocks'],
         }
+        out.update(extras)
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
 
-def run_batch(args):
+def batch_solve(args, world, rank, dev):
     """
     C4: a grid of atmospheres (T_eq x log g x metallicity), 50 layers x 20k bins, 3 species, each
-    iterated to convergence (Grid.emission_spectrum's rule, evaluated on the device) and finished
+    iterated until Grid.emission_spectrum's rule (evaluated on the device) stops it and finished
     with the final emit; atmospheres are sharded over the GPUs with no collective.
-    Metric: converged T-P profiles per second.
+    Returns the record of the metric "converged T-P profiles per second".
     """
     import torch
     import torch.distributed as dist
     from frei_b200 import synthetic
-    from frei_b200.engine import Engine, FREI_F64, shard_range
+    from frei_b200.engine import Engine, FREI_F64
 
-    world = int(os.environ.get('WORLD_SIZE', '1'))
-    rank = int(os.environ.get('RANK', '0'))
-    local_rank = int(os.environ.get('LOCAL_RANK', '0'))
-    torch.cuda.set_device(local_rank)
-    dev = torch.device('cuda', local_rank)
-    if world > 1:
-        dist.init_process_group('nccl', device_id=dev)
     L, n_lam, S = 50, 20_000, 3
     n_side = max(1, round(args.batch ** (1 / 3)))
     B_total = n_side ** 3
@@ -412,13 +550,9 @@ def run_batch(args):
         torch.cuda.synchronize()
 
     # warm-up on the real state, then reset
-    for _ in range(max(3, args.warmup)):
+    for _ in range(3):
         eng.iteration()
     eng.reset(T0, mmr)
-    sampler = ClockSampler(local_rank)
-    sync()
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.launches
     sync()
@@ -427,33 +561,53 @@ def run_batch(args):
     ev1.record()
     sync()
     ms = ev0.elapsed_time(ev1)
-    clocks = sampler.stop() if rank == 0 else None
+    finite = np.isfinite(T).all(axis=1)
     t = torch.tensor([ms], dtype=torch.float64, device=dev)
-    it_sum = torch.tensor([float(iters.sum()), float(iters.max()), float((iters >= args.max_iterations).sum())],
-                          dtype=torch.float64, device=dev)
+    agg = torch.tensor([float(iters.sum()), float((iters >= args.max_iterations).sum()), float(finite.sum()),
+                        float(eng.launches - launches0)], dtype=torch.float64, device=dev)
+    mx = torch.tensor([float(iters.max())], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        agg = [torch.zeros_like(it_sum) for _ in range(world)]
-        dist.all_gather(agg, it_sum)
-        it_sum = torch.stack(agg)
-        tot_it, max_it, capped = float(it_sum[:, 0].sum()), float(it_sum[:, 1].max()), float(it_sum[:, 2].sum())
-    else:
-        tot_it, max_it, capped = [float(x) for x in it_sum]
+        dist.all_reduce(agg, op=dist.ReduceOp.SUM)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
     ms = float(t.item())
+    tot_it, capped, n_finite, launches = [float(x) for x in agg.tolist()]
+    evals = (2 * tot_it + B_total) * (L - 1) * n_lam          # sweeps actually executed
+    del eng, table
+    torch.cuda.empty_cache()
+    return {
+        'metric': 'converged T-P profiles/s', 'value': n_finite / (ms * 1e-3), 'unit': 'profiles/s',
+        'n_gpus': world, 'ms_total': ms, 'scaling': 'strong', 'dtype': 'f64',
+        'workload': f'C4: batch of {B_total} atmospheres (T_eq x log g x metallicity), '
+                    '50 layers x 20k lambda bins, 3 species, full RE solve each (until the convergence '
+                    'rule of frei/core.py:306-318 stops it, then the final emit), batch-sharded, no collective',
+        'atmospheres': B_total, 'converged_finite': int(n_finite),
+        'diverged_nan': int(B_total - n_finite),
+        'hit_iteration_cap': int(capped), 'iteration_cap': args.max_iterations,
+        'mean_iterations': tot_it / B_total, 'max_iterations': float(mx.item()),
+        'all_profiles_per_s': B_total / (ms * 1e-3), 'useful_evals_per_s': evals / (ms * 1e-3),
+        'gpu_launches': int(launches),
+        'note': 'value counts only atmospheres that end with a finite T-P profile; diverged_nan are cold, '
+                'metal-rich corners of the grid where the reference\'s explicit temperature update '
+                'overshoots to T < 0 and then NaN (the CPU oracle does the same); the reference\'s rule '
+                'stops them too, because np.sign(nan) != np.sign(nan) counts as a zero crossing'}
+
+
+def run_batch(args):
+    """--workload C4: the batch record as the JSON line."""
+    import torch.distributed as dist
+    world, rank, local_rank, dev, group = setup_dist()
+    rec = batch_solve(args, world, rank, dev)
     if rank == 0:
-        evals = (2 * tot_it + B_total) * (L - 1) * n_lam          # sweeps actually executed
-        print(json.dumps({
-            'metric': 'converged T-P profiles/s', 'value': B_total / (ms * 1e-3), 'unit': 'profiles/s',
-            'n_gpus': world, 'steps': 1, 'warmup': max(3, args.warmup), 'ms_per_step': ms,
-            'higher_is_better': True, 'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64',
-            'data': 'synthetic',
-            'config': {'workload': f'C4: batch of {B_total} atmospheres (T_eq x log g x metallicity), '
-                                   '50 layers x 20k lambda bins, 3 species, full RE solve each, '
-                                   'batch-sharded (no collective)',
-                       'mean_iterations': tot_it / B_total, 'max_iterations': max_it,
-                       'hit_iteration_cap': capped, 'iteration_cap': args.max_iterations,
-                       'useful_evals_per_s': evals / (ms * 1e-3)},
-            'gpu_launches': eng.launches - launches0, 'clocks': clocks}))
+        out = {'metric': rec['metric'], 'value': rec['value'], 'unit': rec['unit'], 'n_gpus': world,
+               'steps': 1, 'warmup': 3, 'ms_per_step': rec['ms_total'], 'higher_is_better': True,
+               'scaling': 'strong', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+               'config': {k: rec[k] for k in ('workload', 'atmospheres', 'converged_finite', 'diverged_nan',
+                                              'hit_iteration_cap', 'iteration_cap', 'mean_iterations',
+                                              'max_iterations', 'all_profiles_per_s', 'useful_evals_per_s',
+                                              'note')},
+               'gpu_launches': rec['gpu_launches']}
+        print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
 
@@ -469,6 +623,8 @@ def main():
     ap.add_argument('--flux-dtype', type=int, default=64, choices=[32, 64],
                     help='64: fp64 arithmetic (headline); 32: fp32 state and arithmetic, fp64 integrals')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-extras', action='store_true',
+                    help='skip the secondary records (C3 strong scaling, C2 in fp32, C4 batch solve)')
     ap.add_argument('--collective', default='auto', choices=['auto', 'p2p', 'nccl'],
                     help='N > 1: fused peer-memory all-reduce inside the post kernel (p2p) or NCCL')
     ap.add_argument('--workload', default='C2', choices=['C1', 'C2', 'C3', 'C4', 'C5'])

@@ -11,6 +11,7 @@ import os
 
 from . import build as _build
 
+ABI_VERSION = 2          # FREI_B200_ABI_VERSION of include/frei_b200.h
 FREI_EMIT, FREI_ABSORB = 0, 1
 FREI_F32, FREI_F64 = 32, 64
 
@@ -51,7 +52,7 @@ class frei_flux(C.Structure):
 
 
 class frei_p2p(C.Structure):
-    _fields_ = [('peer_bufs', c_void_p), ('peer_flags', c_void_p), ('error', c_void_p),
+    _fields_ = [('peer_bufs', c_void_p), ('error', c_void_p),
                 ('epoch', C.c_uint64), ('rank', c_int32), ('world', c_int32)]
 
 
@@ -97,6 +98,7 @@ SIGNATURES = {
                                         c_void_p]),
     'frei_b200_bin_trapz': (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p,
                                       c_void_p, c_int32, c_void_p, c_void_p]),
+    'frei_b200_fp64_peak': (C.c_int, [c_void_p, c_int64, P(c_double), c_void_p]),
 }
 
 _lib = None
@@ -127,7 +129,7 @@ def load():
         fn = getattr(lib, name)          # AttributeError if a declared symbol is not exported
         fn.restype = res
         fn.argtypes = args
-    if lib.frei_b200_abi_version() != 1:
+    if lib.frei_b200_abi_version() != ABI_VERSION:
         raise FreiError('libfrei_b200.so ABI version mismatch')
     _lib = lib
     return lib

@@ -6,6 +6,8 @@ frei/core.py:263-338) and runs every sweep on the GPU with the flux state,
 tables and per-wavelength constants resident in HBM; only T and dT
 (``n_layers`` doubles each) cross PCIe per iteration.
 """
+import collections
+
 import numpy as np
 
 from . import _cabi
@@ -239,7 +241,7 @@ class Grid(object):
                       self._mmr(T0, P, m_bar_g), g=U.gravity_cgs(pl.g), m_bar=m_bar_g,
                       alpha=pl.alpha, T_star=float(U.value(pl.T_star, 'K')),
                       a_rstar=float(pl.a_rstar), group=group, want_dtaus=want_dtaus,
-                      flux_dtype=self.flux_dtype)
+                      flux_dtype=self.flux_dtype, collective=getattr(self, 'collective', 'auto'))
 
     def emission_spectrum(self, n_timesteps=1, n_zero_crossings=2, convergence_dT=3,
                           group=None, dynamic_chemistry=None, gather='all'):
@@ -282,24 +284,36 @@ class Grid(object):
             # queued back to back and the host looks at the flag only every `check_every`
             # iterations instead of synchronising after each one.  The temperature history is
             # written by the update kernel into a device buffer, one [2][L] slot per iteration.
-            check_every = 4
+            # The host never blocks on a flag: every `check_every` iterations it queues a copy of
+            # the flag into pinned memory behind an event and only looks at copies whose event has
+            # completed, while it keeps the device fed (at most `max_ahead` iterations beyond the
+            # oldest unread flag; iterations queued after the rule has fired cost a launch each).
+            check_every, max_ahead = 4, 16
             eng.enable_batch_convergence(n_zero_crossings, conv_dT)
-            blocks, it, stopped = [], 0, False
+            hist = eng.history_buffer(n_timesteps)             # [n_timesteps][2][B][L], reused across solves
+            flags = eng.flag_ring(max_ahead // check_every + 2)
+            pending, it, stopped = collections.deque(), 0, False
             while it < n_timesteps and not stopped:
-                nb = min(256, n_timesteps - it)
-                hist = torch.zeros((nb, 2, 1, L), dtype=torch.float64, device=eng.device)
-                blocks.append(hist)
-                for j in range(nb):
-                    eng.sweep(FREI_EMIT, T_hist=hist[j, 0])
-                    eng.sweep(FREI_ABSORB, T_hist=hist[j, 1])
-                    it += 1
-                    if it % check_every == 0 and not bool(eng.active.any().item()):
+                eng.sweep(FREI_EMIT, T_hist=hist[it, 0])
+                eng.sweep(FREI_ABSORB, T_hist=hist[it, 1])
+                it += 1
+                if it % check_every == 0:
+                    slot = (it // check_every) % flags.shape[0]
+                    flags[slot].copy_(eng.active[:1], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record()
+                    pending.append((ev, slot, it))
+                if pending and it - pending[0][2] >= max_ahead:
+                    pending[0][0].synchronize()
+                while pending and pending[0][0].query():
+                    _, slot, _ = pending.popleft()
+                    if int(flags[slot, 0]) == 0:
                         stopped = True
-                        break
-            still = bool(eng.active.any().item())
+            still = bool(eng.active.any().item())              # synchronises
+            eng.check_errors()
             self.n_iterations = it if still else int(eng.iterations_done[0].item())
             eng.disable_batch_convergence()
-            h = torch.cat(blocks, dim=0)[:self.n_iterations, :, 0, :].cpu().numpy()   # [n][2][L]
+            h = hist[:self.n_iterations, :, 0, :].cpu().numpy()                       # [n][2][L]
             temp_hists = [h[k].T for k in range(self.n_iterations)]
         for it in range(n_timesteps if dynamic_chemistry else 0):
             if it > 0:
@@ -342,6 +356,7 @@ class Grid(object):
             out[0].copy_(spec_local, non_blocking=True)
             out[1:].copy_(dtaus_local, non_blocking=True)
         final_temps = eng.T[0].cpu().numpy()                   # synchronises the stream
+        eng.check_errors()
         arr = self._outputs.hand_out(out)
         spec, dtaus = arr[0], arr[1:]
         self.engine = eng
@@ -357,7 +372,7 @@ class Grid(object):
         table = self.device_table(group)
         key = (id(table), id(group), T0.shape, U.value(self.lam, 'um').shape,
                U.gravity_cgs(pl.g), m_bar_g, float(pl.alpha), float(U.value(pl.T_star, 'K')),
-               float(pl.a_rstar), P.tobytes(), self.flux_dtype)
+               float(pl.a_rstar), P.tobytes(), self.flux_dtype, getattr(self, 'collective', 'auto'))
         if getattr(self, '_eng_key', None) != key:
             self._eng = self.make_engine(group=group, want_dtaus=True)
             self._eng_key = key

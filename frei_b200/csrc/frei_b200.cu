@@ -1014,9 +1014,12 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
             const int ncol = u.trk_ncol[b];
             int sgn_prev = u.trk_state[li * 2], flips = u.trk_state[li * 2 + 1];
             if (ncol > 0) {
+                // np.sign(diffs[1:]) != np.sign(diffs[:-1]) (core.py:308): a NaN difference compares
+                // unequal to everything, itself included, so an atmosphere whose explicit update has
+                // diverged collects a "sign change" per column and is stopped by the rule (code 3)
                 const double d = Tn - u.trk_T[li];
-                const int sgn = (d > 0.0) - (d < 0.0);
-                if (sgn_prev != 2 && sgn != sgn_prev) ++flips;
+                const int sgn = (d != d) ? 3 : (d > 0.0) - (d < 0.0);
+                if (sgn_prev != 2 && (sgn != sgn_prev || sgn == 3)) ++flips;
                 sgn_prev = sgn;
             }
             u.trk_T[li] = Tn;
@@ -1060,8 +1063,7 @@ struct PostArgs {
     const double* partials; double* chunk_sums; unsigned int* counters; double* sums;
     const uint8_t* active;
     // fused cross-GPU sum over NVLink peer memory (null peer_bufs = single device)
-    double* const* peer_bufs;            // [world] exchange buffers, doubles [2][world][B][L*4]
-    unsigned long long* const* peer_flags;   // [world] arrival flags [2][world][B]
+    unsigned long long* const* peer_bufs;    // [world] exchange buffers, 8-byte words [2][world][B][L*4][2]
     int* p2p_error;
     unsigned long long epoch;
     int rank, world, B;
@@ -1156,39 +1158,42 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
     __threadfence();
     double s2 = cta_column_sum(q.chunk_sums + (int64_t)b * q.nchunks * n, q.nchunks, n, sm_post, G);
     if (q.peer_bufs) {
-        // One-shot all-reduce fused into this kernel: every rank stores its [L][4] integrals into
-        // its slot of every peer's exchange buffer (NVLink P2P stores), publishes an arrival flag
-        // with release semantics at system scope, waits for the flags of all ranks in its own
-        // buffer and adds the slots in rank order — the same order on every rank, so all ranks
-        // get bit-identical sums and apply the identical temperature update.  Slots and flags are
-        // double-buffered by the parity of the sweep counter.
+        // One-shot all-reduce fused into this kernel, flag-in-data ("LL") protocol: every double of
+        // this rank's [L][4] integrals is sent to every rank as two 8-byte words, each holding 32
+        // payload bits and the 32-bit epoch.  An aligned 8-byte store is single-copy atomic, so a
+        // word that shows the current epoch carries valid payload: no fence, no separate flag, no
+        // second trip over NVLink — the receiver polls the words themselves.  (A 16-byte vector
+        // store is two such words; nothing relies on the pair arriving together.)  The
+        // contributions are added in rank order, the same on every rank, so all ranks get
+        // bit-identical sums and apply the identical temperature update.  Slots are
+        // double-buffered by the parity of the epoch: a rank can be at most one sweep ahead of the
+        // slowest one, because its next exchange needs that rank's contribution.
         const int par = (int)(q.epoch & 1ull);
-        const int64_t slot = (((int64_t)par * q.world + q.rank) * q.B + b) * n;
-        if (threadIdx.x < n)
-            for (int r = 0; r < q.world; ++r) q.peer_bufs[r][slot + threadIdx.x] = s2;
-        __threadfence_system();
-        __syncthreads();
-        const int64_t fidx = ((int64_t)par * q.world + q.rank) * q.B + b;
-        if (threadIdx.x < q.world) {
-            unsigned long long* f = q.peer_flags[threadIdx.x] + fidx;
-            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(f), "l"(q.epoch) : "memory");
-        }
-        if (threadIdx.x < q.world) {
-            const unsigned long long* f = q.peer_flags[q.rank] + ((int64_t)par * q.world + threadIdx.x) * q.B + b;
-            unsigned long long v = 0;
-            int spins = 0;
-            for (;;) {
-                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(f) : "memory");
-                if (v == q.epoch) break;
-                if (++spins > (1 << 24)) { if (q.p2p_error) *q.p2p_error = 1; break; }   // ~seconds
-                __nanosleep(200);
-            }
-        }
-        __syncthreads();
+        const unsigned long long fl = (q.epoch & 0xffffffffull) << 32;
         if (threadIdx.x < n) {
-            const double* mine = q.peer_bufs[q.rank] + ((int64_t)par * q.world * q.B + b) * n + threadIdx.x;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(s2);
+            const unsigned long long w0 = (bits & 0xffffffffull) | fl, w1 = (bits >> 32) | fl;
+            const int64_t slot = ((((int64_t)par * q.world + q.rank) * q.B + b) * n + threadIdx.x) * 2;
+            for (int r = 0; r < q.world; ++r) {
+                const int dst = (q.rank + r) % q.world;      // spread the first stores over the links
+                asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};"
+                             ::"l"(q.peer_bufs[dst] + slot), "l"(w0), "l"(w1) : "memory");
+            }
             double tot = 0.0;
-            for (int r = 0; r < q.world; ++r) tot += mine[(int64_t)r * q.B * n];
+            bool timed_out = false;
+            for (int r = 0; r < q.world; ++r) {
+                const unsigned long long* src =
+                    q.peer_bufs[q.rank] + ((((int64_t)par * q.world + r) * q.B + b) * n + threadIdx.x) * 2;
+                unsigned long long a0 = 0, a1 = 0;
+                for (long long spins = 0;; ++spins) {
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];"
+                                 : "=l"(a0), "=l"(a1) : "l"(src) : "memory");
+                    if ((a0 & 0xffffffff00000000ull) == fl && (a1 & 0xffffffff00000000ull) == fl) break;
+                    if (spins > (1ll << 27)) { timed_out = true; break; }     // seconds: a peer is gone
+                }
+                tot += __longlong_as_double((long long)((a0 & 0xffffffffull) | (a1 << 32)));
+            }
+            if (timed_out && q.p2p_error) *q.p2p_error = 1;   // the host raises at its next poll
             s2 = tot;
         }
     }
@@ -1508,13 +1513,12 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
     q.plan_hdr = ws_plan_hdr(ws, atm->B, atm->L, n_lam);
     q.sums = ws->sums;
     q.active = atm->active;
-    q.peer_bufs = nullptr; q.peer_flags = nullptr; q.p2p_error = nullptr;
+    q.peer_bufs = nullptr; q.p2p_error = nullptr;
     q.epoch = 0; q.rank = 0; q.world = 1; q.B = atm->B;
     if (p2p) {
-        ARG_TRY(p2p->peer_bufs && p2p->peer_flags && p2p->world >= 1 && p2p->world <= 64);
-        ARG_TRY(p2p->rank >= 0 && p2p->rank < p2p->world && p2p->epoch > 0);
-        q.peer_bufs = (double* const*)p2p->peer_bufs;
-        q.peer_flags = (unsigned long long* const*)p2p->peer_flags;
+        ARG_TRY(p2p->peer_bufs && p2p->world >= 1 && p2p->world <= 64);
+        ARG_TRY(p2p->rank >= 0 && p2p->rank < p2p->world && (p2p->epoch & 0xffffffffull) != 0);
+        q.peer_bufs = (unsigned long long* const*)p2p->peer_bufs;
         q.p2p_error = p2p->error; q.epoch = p2p->epoch; q.rank = p2p->rank; q.world = p2p->world;
     }
     q.do_update = do_update; q.do_prep = do_prep;

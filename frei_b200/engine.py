@@ -209,10 +209,10 @@ class Engine:
         self._hist_host = None
         self.launches = 0
         self._p2p = None
+        self._graph = None
         if group is not None and collective in ('auto', 'p2p'):
             self._setup_p2p(required=(collective == 'p2p'))
         self._records_stale = True     # level records must be rebuilt before the next sweep
-        self._graph = None
         self.sweep_events = None        # list of (start, end) CUDA events around the sweep kernel
         self._build_structs()
 
@@ -220,38 +220,56 @@ class Engine:
     def _setup_p2p(self, required=False):
         """
         Exchange buffers in symmetric (peer-mapped) memory for the one-launch
-        reduce + all-reduce + update (``frei_b200_post_p2p``).  Falls back to the NCCL
-        all-reduce between two launches when symmetric memory is unavailable.
+        reduce + all-reduce + update (``frei_b200_post_p2p``).  All ranks must end up with the
+        same collective: a rank whose rendezvous failed while its peers spin on words that never
+        arrive would hang the job, so the outcome is agreed on with an all-reduce (MIN) and every
+        rank falls back to the NCCL all-reduce between two launches together — with a warning.
         """
         torch = _torch()
+        import warnings
         import torch.distributed as dist
+        p2p, why = None, ''
         try:
             import torch.distributed._symmetric_memory as symm
             world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
-            n = self.B * self.L * 4
-            buf = symm.empty(2 * world * n, dtype=torch.float64, device=self.device)
-            flags = symm.empty(2 * world * self.B, dtype=torch.int64, device=self.device)
+            words = 2 * world * self.B * self.L * 4 * 2        # [2][world][B][L*4][2] 8-byte words
+            buf = symm.empty(words, dtype=torch.int64, device=self.device)
             buf.zero_()
-            flags.zero_()
             hb = symm.rendezvous(buf, self.group)
-            hf = symm.rendezvous(flags, self.group)
             torch.cuda.synchronize(self.device)
-            dist.barrier(group=self.group)
-            self._p2p = dict(
-                buf=buf, flags=flags, hb=hb, hf=hf, rank=rank, world=world, epoch=0,
-                bufs=torch.tensor(list(hb.buffer_ptrs), dtype=torch.int64, device=self.device),
-                flgs=torch.tensor(list(hf.buffer_ptrs), dtype=torch.int64, device=self.device),
-                err=torch.zeros(1, dtype=torch.int32, device=self.device))
-        except Exception:
-            if required:
-                raise
-            self._p2p = None
+            p2p = dict(buf=buf, hb=hb, rank=rank, world=world, epoch=0,
+                       bufs=torch.tensor(list(hb.buffer_ptrs), dtype=torch.int64, device=self.device),
+                       err=torch.zeros(1, dtype=torch.int32, device=self.device))
+        except Exception as exc:                               # no symmetric memory on this system
+            why = repr(exc)
+        ok = torch.tensor([1 if p2p is not None else 0], dtype=torch.int32, device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self.group)       # also the barrier after zero_()
+        if int(ok.item()) == 1:
+            self._p2p = p2p
+            return
+        self._p2p = None
+        msg = ('frei_b200: peer-memory exchange unavailable on at least one rank'
+               + (f' (this rank: {why})' if why else '') + '; all ranks use the NCCL all-reduce')
+        if required:
+            raise _cabi.FreiError(msg)
+        warnings.warn(msg)
+
+    def check_errors(self):
+        """
+        Raise if the fused cross-GPU exchange timed out on this rank (a peer did not deliver its
+        integrals): the sums, and every temperature since, are invalid.  Synchronises the stream;
+        called wherever the host already waits for the device.
+        """
+        if self._p2p is not None and int(self._p2p['err'].item()) != 0:
+            raise _cabi.FreiError('frei_b200: peer-memory all-reduce timed out waiting for a rank; '
+                                  'temperatures on this rank are invalid')
 
     # -- plumbing -----------------------------------------------------------
     def _stream(self):
         return _torch().cuda.current_stream(self.device).cuda_stream
 
     def _build_structs(self):
+        self._graph = None          # a captured iteration holds the old structs' pointers
         n = self.n_lam
         self._tab = self.table.struct()
         self._spec = _cabi.frei_spectral(self.c1.data_ptr(), self.c2.data_ptr(),
@@ -349,8 +367,12 @@ class Engine:
         for it in range(n_timesteps):
             self.iteration()
             n_done += 1
-            if (it + 1) % check_every == 0 and not bool(self.active.any().item()):
-                break
+            if (it + 1) % check_every == 0:
+                done = not bool(self.active.any().item())
+                self.check_errors()
+                if done:
+                    break
+        self.check_errors()
         iters = self.iterations_done.cpu().numpy().copy()
         still = self.active.cpu().numpy().astype(bool)
         iters[still] = n_done                                  # stopped by n_timesteps
@@ -386,6 +408,26 @@ class Engine:
         self._graph = graph
         return True
 
+    def history_buffer(self, n_iterations):
+        """Device buffer [n][2][B][L] for the temperature history of up to n iterations (cached)."""
+        torch = _torch()
+        buf = getattr(self, '_hist_buf', None)
+        if buf is None or buf.shape[0] < n_iterations:
+            buf = torch.empty((max(n_iterations, 32), 2, self.B, self.L), dtype=torch.float64,
+                              device=self.device)
+            self._hist_buf = buf
+        return buf
+
+    def flag_ring(self, n):
+        """Pinned host ring [n][1] of uint8 for asynchronous copies of the convergence flag."""
+        torch = _torch()
+        ring = getattr(self, '_flag_ring', None)
+        if ring is None or ring.shape[0] < n:
+            ring = torch.ones((n, 1), dtype=torch.uint8).pin_memory()
+            self._flag_ring = ring
+        ring.fill_(1)
+        return ring
+
     def read_history(self):
         """(T after emit, T after absorb, dT of the absorb sweep) as host arrays [B][L]; syncs."""
         torch = _torch()
@@ -393,6 +435,7 @@ class Engine:
             self._hist_host = torch.empty((3, self.B, self.L), dtype=torch.float64).pin_memory()
         self._hist_host.copy_(self.hist, non_blocking=True)
         torch.cuda.current_stream(self.device).synchronize()
+        self.check_errors()
         h = self._hist_host.numpy()
         return h[0].copy(), h[1].copy(), h[2].copy()
 
@@ -470,8 +513,10 @@ class Engine:
         elif self._p2p is not None:
             p = self._p2p
             p['epoch'] += 1
-            arg = _cabi.frei_p2p(p['bufs'].data_ptr(), p['flgs'].data_ptr(), p['err'].data_ptr(),
-                                 p['epoch'], p['rank'], p['world'])
+            if p['epoch'] & 0xffffffff == 0:                   # the low word is the in-band flag: never 0
+                p['epoch'] += 1
+            arg = _cabi.frei_p2p(p['bufs'].data_ptr(), p['err'].data_ptr(), p['epoch'], p['rank'],
+                                 p['world'])
             _cabi.check(self.lib.frei_b200_post_p2p(C.byref(self._tab), C.byref(self._atm),
                                                     C.byref(self._ws), self.n_lam, direction,
                                                     float(alpha_override), hist_ptr, 1,

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define FREI_B200_ABI_VERSION 1
+#define FREI_B200_ABI_VERSION 2
 
 enum {
     FREI_OK = 0,
@@ -221,17 +221,19 @@ int frei_b200_post(const frei_table* tab, const frei_atmosphere* atm, const frei
                    int32_t prep_next, void* stream);
 
 /* Wavelength-sharded mode without a separate collective: reduce + all-reduce + update_T
- * (+ layer_prep) in ONE launch.  Every rank stores its [B][L][4] integrals into all peers'
- * exchange buffers over NVLink peer memory, publishes a system-scope flag, waits for all ranks
- * and adds the contributions in rank order (bit-identical sums on every rank).
- * peer_bufs / peer_flags: device arrays of `world` device pointers (peer-mapped, e.g. from
- * torch.distributed._symmetric_memory) to each rank's doubles [2][world][B][L*4] and
- * uint64 [2][world][B], both zero-initialised before the first sweep.  epoch = 1, 2, 3, ...
- * must advance identically on all ranks (one per sweep).  *error (device int, nullable) is set
- * if a peer does not arrive within a few seconds. */
+ * (+ layer_prep) in ONE launch.  Every rank stores its [B][L][4] integrals into all ranks'
+ * exchange buffers over NVLink peer memory as self-validating 8-byte words (32 payload bits +
+ * the 32-bit epoch: no fence and no separate flag), polls its own buffer until the words of all
+ * ranks carry the current epoch and adds the contributions in rank order (bit-identical sums on
+ * every rank).
+ * peer_bufs: device array of `world` device pointers (peer-mapped, e.g. from
+ * torch.distributed._symmetric_memory) to each rank's buffer of 2 * world * B * L*4 * 2 8-byte
+ * words, zero-initialised before the first sweep.  epoch = 1, 2, 3, ... must advance identically on
+ * all ranks (one per sweep; its low 32 bits must not be 0).  *error (device int, nullable) is set
+ * to 1 if a peer does not arrive within a few seconds; the sums are then invalid and the caller
+ * must check it before using T (frei_b200/engine.py: Engine.check_errors). */
 typedef struct {
     void* const* peer_bufs;
-    void* const* peer_flags;
     int32_t* error;
     uint64_t epoch;
     int32_t rank, world;
@@ -281,6 +283,13 @@ int frei_b200_diagnostics(const double* d_dtaus, const double* d_spec, const dou
                           const double* d_w, const double* d_P_bar, const double* d_T, int32_t L,
                           int64_t n_lam, double* d_pressure_milne, double* d_cf, double* d_scratch,
                           double* d_sums, void* stream);
+
+/* Measurement aid (bench.py): thread-level fp64 fused multiply-adds per second this device
+ * sustains with register operands and 16 resident warps per scheduler (best of three timed
+ * launches, CUDA events on `stream`, synchronises).  It is the ceiling the fp64 sweep is compared
+ * with; MEASURED_PEAKS.json has no fp64 entry.  d_scratch: at least 2048 doubles per SM. */
+int frei_b200_fp64_peak(double* d_scratch, int64_t scratch_doubles, double* h_dfma_per_s,
+                        void* stream);
 
 #ifdef __cplusplus
 }

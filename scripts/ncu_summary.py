@@ -1,7 +1,9 @@
 """Summarise an `ncu --set full` report of the sweep kernel into profiles/ (run where ncu is installed).
-usage: python scripts/ncu_summary.py REPORT.ncu-rep CAPTURE_TAG "what was captured" [--write]
+usage: python scripts/ncu_summary.py REPORT.ncu-rep CAPTURE_TAG "what was captured" [--write [KEY]]
 Prints one JSON object per captured launch; --write appends them to
-profiles/r01_sweep_kernel_ncu_summary.json and refreshes profiles/traffic.json (C2, fp64, 1 GPU)."""
+profiles/r02_sweep_kernel_ncu_summary.json and refreshes the entry KEY (default C2_tab64_flux64_n1)
+of profiles/traffic.json: DRAM bytes and executed fp64 thread operations per launch, which
+bench.py turns into roofline.traffic and the fp64 flop count of its roofline."""
 import csv
 import io
 import json
@@ -38,7 +40,7 @@ def main():
     rows = list(csv.reader(io.StringIO(out)))
     header, units = rows[0], rows[1]
     col = {h: i for i, h in enumerate(header)}
-    res, traffic = [], []
+    res, traffic, ops = [], [], []
     for r in rows[2:]:
         d = {'capture': tag, 'what': what, 'Kernel Name': r[col['Kernel Name']]}
         for k in KEEP:
@@ -51,20 +53,35 @@ def main():
         rd, wr = 'dram__bytes_read.sum', 'dram__bytes_write.sum'
         if rd in col and wr in col:
             traffic.append(to_bytes(r[col[rd]], units[col[rd]]) + to_bytes(r[col[wr]], units[col[wr]]))
+        # executed fp64 thread instructions of the launch: rate per elapsed cycle x elapsed cycles
+        cyc = 'smsp__cycles_elapsed.avg'
+        o = {}
+        for op in ('dfma', 'dmul', 'dadd'):
+            k = f'smsp__sass_thread_inst_executed_op_{op}_pred_on.sum.per_cycle_elapsed'
+            if k in col and cyc in col and r[col[k]]:
+                o[op] = float(r[col[k]].replace(',', '')) * float(r[col[cyc]].replace(',', ''))
+        if len(o) == 3:
+            d['fp64_thread_ops'] = {k: round(v) for k, v in o.items()}
+            ops.append(o)
         res.append(d)
     print(json.dumps(res, indent=1))
     if '--write' in sys.argv:
-        p = os.path.join(ROOT, 'profiles', 'r01_sweep_kernel_ncu_summary.json')
-        allc = json.load(open(p)) + res
+        p = os.path.join(ROOT, 'profiles', 'r02_sweep_kernel_ncu_summary.json')
+        allc = (json.load(open(p)) if os.path.exists(p) else []) + res
+        wi = sys.argv.index('--write')
+        key = sys.argv[wi + 1] if len(sys.argv) > wi + 1 else 'C2_tab64_flux64_n1'
         json.dump(allc, open(p, 'w'), indent=1)
         if traffic:
             tp = os.path.join(ROOT, 'profiles', 'traffic.json')
             t = json.load(open(tp))
-            t['C2_tab64_flux64_n1'] = {
+            t[key] = {
                 'bytes_per_launch': sum(traffic) / len(traffic),
                 'per_launch': traffic,
-                'source': f'profiles/r01_sweep_kernel_ncu_summary.json capture {tag} '
-                          f'(ncu --set full of scripts/prof_sweep.py, C2)'}
+                'source': f'profiles/r02_sweep_kernel_ncu_summary.json capture {tag} '
+                          f'(ncu --set full of scripts/prof_sweep.py)'}
+            if ops:      # thread-level fp64 instructions per launch (DFMA = 2 flops, DMUL / DADD = 1)
+                t[key]['fp64_thread_ops_per_launch'] = {
+                    k: sum(o[k] for o in ops) / len(ops) for k in ('dfma', 'dmul', 'dadd')}
             json.dump(t, open(tp, 'w'), indent=1)
 
 

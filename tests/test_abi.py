@@ -37,7 +37,7 @@ def test_struct_layouts_match_header():
 
 def test_abi_version_and_workspace_query():
     lib = _cabi.load()
-    assert lib.frei_b200_abi_version() == 1
+    assert lib.frei_b200_abi_version() == 2
     sizes = [C.c_int64() for _ in range(4)]
     rc = lib.frei_b200_workspace_bytes(2, 50, 3, 200000, *[C.byref(s) for s in sizes])
     assert rc == 0
