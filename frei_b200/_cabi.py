@@ -96,8 +96,10 @@ SIGNATURES = {
     'frei_b200_diagnostics': (C.c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_int32, c_int64, c_void_p, c_void_p, c_void_p, c_void_p,
                                         c_void_p]),
-    'frei_b200_bin_trapz': (C.c_int, [c_void_p, c_int32, c_int64, c_int64, c_int64, c_void_p, c_void_p,
-                                      c_void_p, c_int32, c_void_p, c_void_p]),
+    'frei_b200_bin_trapz': (C.c_int, [c_void_p, c_int32, c_void_p, c_int64, c_int64, c_int64, c_void_p,
+                                      c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    'frei_b200_regrid': (C.c_int, [c_void_p, c_int32, c_int32, c_int64, c_void_p, c_int32, c_void_p,
+                                   c_int32, c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     'frei_b200_fp64_peak': (C.c_int, [c_void_p, c_int64, P(c_double), c_void_p]),
 }
 

@@ -55,25 +55,10 @@ def runs_by_bin(codes, n_bins):
     return starts.astype(np.int64), ends.astype(np.int64), first
 
 
-def groupby_bins_agg(array, group, bins, func='trapz', fill_value=0, dtype=None, **cut_kwargs):
-    """
-    Aggregate ``array[..., n_samples]`` over the bins of ``group[n_samples]`` — the reference's
-    ``groupby_bins_agg`` (frei/interp.py:270-307) for its only call site, ``func=np.trapz`` /
-    ``'trapz'``.  ``bins`` are the n_bins + 1 edges (``Grid.wl_bins``).  Returns
-    ``[..., n_bins]`` with the bin centres in ``.wavelength``.  Accepts numpy arrays, torch CUDA
-    tensors (no copy) or xarray-like objects (``.values``).
-    """
+def _device_samples(array):
+    """Samples as a contiguous CUDA tensor [..., n] (fp32 stays fp32; everything else fp64)."""
     import torch
-    if cut_kwargs:
-        raise NotImplementedError('pandas.cut options other than the defaults are not used by frei')
-    if not (func == 'trapz' or func is getattr(np, 'trapz', None) or func is getattr(np, 'trapezoid', None)):
-        raise NotImplementedError("only func='trapz' is on frei's path (frei/opacity.py:137-139)")
-    lib = _cabi.load()
-    _cabi.require_cuda()
     dev = torch.device('cuda', torch.cuda.current_device())
-    g = np.asarray(getattr(group, 'values', group), dtype=np.float64).ravel()
-    bins = np.asarray(getattr(bins, 'value', bins), dtype=np.float64)
-    n_bins = bins.shape[0] - 1
     if torch.is_tensor(array):
         a = array.to(dev)
     else:
@@ -83,7 +68,23 @@ def groupby_bins_agg(array, group, bins, func='trapz', fill_value=0, dtype=None,
         a = torch.from_numpy(np.ascontiguousarray(a_np)).to(dev)
     if a.dtype not in (torch.float32, torch.float64):
         a = a.double()
-    a = a.contiguous()
+    return a.contiguous()
+
+
+def bin_trapz_device(a, group, bins, positions=False):
+    """
+    Trapezoid sum of the samples ``a[..., n]`` (CUDA tensor) per bin of ``group[n]``: unit spacing
+    (``positions=False``: the reference's Trapz aggregation, frei/interp.py:174-194) or with the
+    sample positions ``group`` themselves as x (xarray's ``integrate``, frei/opacity.py:39).
+    Returns ``(out[..., n_bins] fp64 CUDA tensor, first)`` with ``first`` the CSR run offsets per
+    bin (``first[b] == first[b + 1]``: no pair of consecutive samples fell into bin b).
+    """
+    import torch
+    lib = _cabi.load()
+    _cabi.require_cuda()
+    dev = a.device
+    g = np.asarray(group, dtype=np.float64).ravel()
+    n_bins = bins.shape[0] - 1
     lead = tuple(a.shape[:-1])
     n = a.shape[-1]
     if n != g.shape[0]:
@@ -94,16 +95,39 @@ def groupby_bins_agg(array, group, bins, func='trapz', fill_value=0, dtype=None,
     d_s = torch.from_numpy(np.ascontiguousarray(starts) if starts.size else np.zeros(1, np.int64)).to(dev)
     d_e = torch.from_numpy(np.ascontiguousarray(ends) if ends.size else np.zeros(1, np.int64)).to(dev)
     d_f = torch.from_numpy(first).to(dev)
+    d_x = torch.from_numpy(g).to(dev) if positions else None
     out = torch.empty((rows, n_bins), dtype=torch.float64, device=dev)
     st = torch.cuda.current_stream(dev).cuda_stream
     for r0 in range(0, rows, 65535):
         r1 = min(rows, r0 + 65535)
         _cabi.check(lib.frei_b200_bin_trapz(
-            a2[r0:r1].data_ptr(), FREI_F32 if a.dtype == torch.float32 else FREI_F64, r1 - r0, n, n,
-            d_s.data_ptr(), d_e.data_ptr(), d_f.data_ptr(), n_bins, out[r0:r1].data_ptr(), st))
-    res = out.reshape(lead + (n_bins,))
+            a2[r0:r1].data_ptr(), FREI_F32 if a.dtype == torch.float32 else FREI_F64, _cabi.ptr(d_x),
+            r1 - r0, n, n, d_s.data_ptr(), d_e.data_ptr(), d_f.data_ptr(), n_bins,
+            out[r0:r1].data_ptr(), st))
+    return out.reshape(lead + (n_bins,)), first
+
+
+def groupby_bins_agg(array, group, bins, func='trapz', fill_value=0, dtype=None, **cut_kwargs):
+    """
+    Aggregate ``array[..., n_samples]`` over the bins of ``group[n_samples]`` — the reference's
+    ``groupby_bins_agg`` (frei/interp.py:270-307) for its only call site, ``func=np.trapz`` /
+    ``'trapz'``.  ``bins`` are the n_bins + 1 edges (``Grid.wl_bins``).  Returns
+    ``[..., n_bins]`` with the bin centres in ``.wavelength``.  Accepts numpy arrays, torch CUDA
+    tensors (no copy) or xarray-like objects (``.values``).  Sums are accumulated in fp64 (the
+    reference accumulates float32 samples in float32, frei/interp.py:57, 201-202).
+    """
+    import torch
+    if cut_kwargs:
+        raise NotImplementedError('pandas.cut options other than the defaults are not used by frei')
+    if not (func == 'trapz' or func is getattr(np, 'trapz', None) or func is getattr(np, 'trapezoid', None)):
+        raise NotImplementedError("only func='trapz' is on frei's path (frei/opacity.py:137-139)")
+    _cabi.require_cuda()
+    g = np.asarray(getattr(group, 'values', group), dtype=np.float64).ravel()
+    bins = np.asarray(getattr(bins, 'value', bins), dtype=np.float64)
+    a = _device_samples(array)
+    res, first = bin_trapz_device(a, g, bins)
     if fill_value != 0:
-        empty = torch.from_numpy(first[1:] == first[:-1]).to(dev)
+        empty = torch.from_numpy(first[1:] == first[:-1]).to(res.device)
         res[..., empty] = fill_value
     if torch.is_tensor(array):
         return res

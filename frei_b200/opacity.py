@@ -168,28 +168,91 @@ def nearest_index(axis, query):
     return order[np.searchsorted(mids, np.asarray(query, dtype=np.float64), side='left')]
 
 
-def bin_and_regrid(opacity, wavelength_um, src_T, src_P, temperatures, pressures, wl_bins):
+def _regrid_device(binned, src_T, src_P, temperatures, pressures, lerp=None):
     """
-    One species of ``binned_opacity`` (groupies=True branch, frei/opacity.py:128-146): crop to the
-    bin range, unit-spacing trapezoid sum per wavelength bin (GPU), times bin width times 1e-3,
-    then nearest-neighbour lookup onto the Grid's (T, P).  Returns an OpacityTable with dims
-    (temperature, pressure, wavelength).
+    ``frei_b200_regrid``: nearest-neighbour (T, P) lookup of the Grid's nodes in the source grid
+    and (``lerp = (x_src, x_new)``) linear interpolation with extrapolation along wavelength, both
+    in scipy's interp1d arithmetic as xarray applies it (frei/opacity.py:141-146, 163-166).
+    binned: CUDA tensor [nT][nP][nb] fp64.  Returns a CUDA tensor [mT][mP][m].
     """
     import torch
-    from .interp import groupby_bins_agg, bin_centres
-    wl_bins = U.value(wl_bins, 'um')
+    from . import _cabi
+    lib = _cabi.load()
+    dev = binned.device
+    nT, nP, nb = binned.shape
+    iT = torch.from_numpy(nearest_index(src_T, temperatures).astype(np.int32)).to(dev)
+    iP = torch.from_numpy(nearest_index(src_P, pressures).astype(np.int32)).to(dev)
+    j0 = dx = t = None
+    m = nb
+    if lerp is not None:
+        x, x_new = (np.asarray(v, dtype=np.float64) for v in lerp)
+        if x.shape[0] != nb or nb < 2:
+            raise ValueError('linear interpolation along wavelength needs at least two source bins')
+        hi = np.clip(np.searchsorted(x, x_new), 1, nb - 1)               # scipy interp1d._call_linear
+        lo = hi - 1
+        j0 = torch.from_numpy(lo.astype(np.int32)).to(dev)
+        dx = torch.from_numpy(x[hi] - x[lo]).to(dev)
+        t = torch.from_numpy(x_new - x[lo]).to(dev)
+        m = x_new.shape[0]
+    out = torch.empty((iT.shape[0], iP.shape[0], m), dtype=torch.float64, device=dev)
+    _cabi.check(lib.frei_b200_regrid(binned.contiguous().data_ptr(), nT, nP, nb, iT.data_ptr(), iT.shape[0],
+                                     iP.data_ptr(), iP.shape[0], _cabi.ptr(j0), _cabi.ptr(dx), _cabi.ptr(t),
+                                     m, out.data_ptr(), torch.cuda.current_stream(dev).cuda_stream))
+    return out
+
+
+def bin_and_regrid(opacity, wavelength_um, src_T, src_P, temperatures, pressures, wl_bins, lam=None,
+                   groupies=True):
+    """
+    One species of ``binned_opacity`` on the GPU.  ``opacity[T, P, n]`` are line-by-line samples at
+    ascending ``wavelength_um``.
+
+    groupies=True (frei/opacity.py:128-146): crop to the bin range, unit-spacing trapezoid sum per
+    wavelength bin, times bin width times 1e-3, then nearest-neighbour lookup onto the Grid's
+    (T, P); wavelength coordinate = the bin centres of ``pandas.cut``'s labels.
+
+    groupies=False (frei/opacity.py:29-40, 150-167; the default of ``Grid.load_opacities``): per
+    bin with at least one sample, the trapezoid integral over wavelength of the nearest (T, P)
+    node divided by the wavelength span of the bin's samples, placed at their mean wavelength;
+    then linear interpolation with extrapolation onto ``lam``.  A bin with a single sample is 0/0 =
+    NaN there, as in the reference.
+
+    Returns an OpacityTable with dims (temperature, pressure, wavelength).
+    """
+    import torch
+    from .interp import bin_trapz_device, bin_centres, cut_codes, _device_samples
+    wl_bins = np.asarray(U.value(wl_bins, 'um'), dtype=np.float64)
     wl = np.asarray(wavelength_um, dtype=np.float64)
-    keep = (wl > wl_bins.min()) & (wl < wl_bins.max())             # :131-135
-    dev = torch.device('cuda', torch.cuda.current_device())
-    a = torch.from_numpy(np.ascontiguousarray(np.asarray(opacity)[..., keep])).to(dev)
-    binned = groupby_bins_agg(a, wl[keep], wl_bins, func='trapz')  # device tensor [T, P, n_bins]
-    width = torch.from_numpy((wl_bins[1:] - wl_bins[:-1]) * 1e-3).to(dev)     # :139
-    binned = binned * width
-    iT = torch.from_numpy(nearest_index(src_T, U.value(temperatures, 'K'))).to(dev)
-    iP = torch.from_numpy(nearest_index(src_P, U.value(pressures, 'bar'))).to(dev)
-    out = binned.index_select(0, iT).index_select(1, iP).cpu().numpy()
-    tab = OpacityTable(np.transpose(out, (1, 0, 2)), U.value(pressures, 'bar'),
-                       U.value(temperatures, 'K'), bin_centres(wl_bins))
+    T_new, P_new = U.value(temperatures, 'K'), U.value(pressures, 'bar')
+    if groupies:
+        keep = (wl > wl_bins.min()) & (wl < wl_bins.max())             # :131-135
+        a = _device_samples(np.asarray(opacity)[..., keep])
+        binned, _ = bin_trapz_device(a, wl[keep], wl_bins)             # [T, P, n_bins]
+        width = torch.from_numpy((wl_bins[1:] - wl_bins[:-1]) * 1e-3).to(binned.device)      # :139
+        out = _regrid_device(binned * width, src_T, src_P, T_new, P_new)
+        centres = bin_centres(wl_bins)
+    else:
+        if lam is None:
+            raise ValueError('groupies=False interpolates onto lam: pass the wavelength grid')
+        if np.any(np.diff(wl) < 0):
+            raise ValueError('wavelength samples must be ascending')
+        codes = cut_codes(wl, wl_bins)
+        inside = codes >= 0
+        a = _device_samples(np.asarray(opacity)[..., inside])
+        integ, first = bin_trapz_device(a, wl[inside], wl_bins, positions=True)
+        occupied = np.flatnonzero(np.bincount(codes[inside], minlength=wl_bins.shape[0] - 1))
+        # per occupied bin: span and mean of its samples (groupby_bins skips empty bins, :155-160)
+        c = codes[inside]
+        w_in = wl[inside]
+        lo = np.searchsorted(c, occupied, side='left')
+        hi = np.searchsorted(c, occupied, side='right')
+        span = w_in[hi - 1] - w_in[lo]                                 # wl.max() - wl.min(), :38
+        mean = np.array([w_in[s:e].mean() for s, e in zip(lo, hi)])    # wl.mean(), :40
+        sel = torch.from_numpy(occupied).to(integ.device)
+        binned = integ.index_select(2, sel) / torch.from_numpy(span).to(integ.device)       # 0/0 -> NaN
+        out = _regrid_device(binned, src_T, src_P, T_new, P_new, lerp=(mean, U.value(lam, 'um')))
+        centres = np.asarray(U.value(lam, 'um'), dtype=np.float64)
+    tab = OpacityTable(np.transpose(out.cpu().numpy(), (1, 0, 2)), P_new, T_new, centres)
     tab.dims = ('pressure', 'temperature', 'wavelength')
     return tab
 
@@ -197,7 +260,7 @@ def bin_and_regrid(opacity, wavelength_um, src_T, src_P, temperatures, pressures
 def binned_opacity(temperatures, pressures, wl_bins, lam, groupies=True, species=None, path=None):
     """
     Opacity tables of all available species binned to the Grid's wavelengths — signature of
-    frei/opacity.py:66-69.  ``path`` is a glob of HELIOS-K ``.bin`` directories named
+    frei/opacity.py:66-69, both branches (``groupies``: see :func:`bin_and_regrid`).  ``path`` is a glob of HELIOS-K ``.bin`` directories named
     ``<isotopologue>_*`` (the reference reads the netCDF files it wrote from those directories;
     netCDF is not available here, the ``.bin`` payload is identical).
     """
@@ -216,5 +279,6 @@ def binned_opacity(temperatures, pressures, wl_bins, lam, groupies=True, species
     results = {}
     for name, d in zip(iso, dirs):
         T, P, wl, grid = read_opacity_dir(d)
-        results[name] = bin_and_regrid(grid, wl, T, P, temperatures, pressures, wl_bins)
+        results[name] = bin_and_regrid(grid, wl, T, P, temperatures, pressures, wl_bins, lam=lam,
+                                       groupies=groupies)
     return results

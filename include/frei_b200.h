@@ -252,16 +252,31 @@ int frei_b200_sweep_step(const frei_table* tab, const frei_spectral* spec,
                          int32_t prep_first, int32_t prep_next, void* stream);
 
 /* Load-time wavelength binning (frei/interp.py:156-202, 270-307 as called from
- * frei/opacity.py:137-139): unit-spacing trapezoid sum of consecutive samples that fall in the
- * same bin, for every leading (temperature, pressure) row.
+ * frei/opacity.py:137-139): trapezoid sum of consecutive samples that fall in the same bin, for
+ * every leading (temperature, pressure) row.
  * d_a: [n_rows][row_stride] samples (FREI_F32 | FREI_F64), n_samples <= row_stride;
+ * d_x: NULL = unit sample spacing (the reference's Trapz aggregation, x = None), else the sample
+ *   positions [n_samples]: trapezoids of width x[i+1] - x[i] (xarray's integrate('wavelength') of
+ *   the groupies=False branch, frei/opacity.py:29-40);
  * runs of equal consecutive bin codes [run_start[r], run_end[r]) grouped by bin:
  * bin b owns runs bin_first_run[b] .. bin_first_run[b+1]-1 (CSR, n_bins + 1 entries);
  * d_out: [n_rows][n_bins] doubles. */
-int frei_b200_bin_trapz(const void* d_a, int32_t dtype, int64_t n_rows, int64_t n_samples,
-                        int64_t row_stride, const int64_t* d_run_start,
+int frei_b200_bin_trapz(const void* d_a, int32_t dtype, const double* d_x, int64_t n_rows,
+                        int64_t n_samples, int64_t row_stride, const int64_t* d_run_start,
                         const int64_t* d_run_end, const int32_t* d_bin_first_run,
                         int32_t n_bins, double* d_out, void* stream);
+
+/* Load-time regridding of a binned table onto the Grid (frei/opacity.py:141-146, 31-33, 163-166):
+ * d_out [mT][mP][m] <- d_binned [nT][nP][nb] at the source nodes d_src_T [mT], d_src_P [mP] (the
+ * nearest-neighbour indices, host-computed with scipy's interp1d(kind='nearest') rule).
+ * d_j0 == NULL: the wavelength axis is copied (m == nb).  Otherwise linear interpolation with
+ * extrapolation along wavelength in scipy's interp1d form: between source columns d_j0[j] and
+ * d_j0[j] + 1, y = (y_hi - y_lo) / d_dx[j] * d_t[j] + y_lo with d_dx = x_hi - x_lo and
+ * d_t = x_new - x_lo (NaN nodes propagate as in scipy). */
+int frei_b200_regrid(const double* d_binned, int32_t nT, int32_t nP, int64_t nb,
+                     const int32_t* d_src_T, int32_t mT, const int32_t* d_src_P, int32_t mP,
+                     const int32_t* d_j0, const double* d_dx, const double* d_t, int64_t m,
+                     double* d_out, void* stream);
 
 /* Device-side post-processing of a finished solve, one thread per wavelength of
  * this device's slice; nothing but three sums has to leave the GPU for T_eff.

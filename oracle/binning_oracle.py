@@ -10,7 +10,15 @@ import numpy as np
 import pandas as pd
 
 
-def groupby_bins_agg(array, group, bins, fill_value=0):
+def groupby_bins_agg(array, group, bins, fill_value=0, keep_dtype=False):
+    """
+    keep_dtype=True replays the reference's accumulator type: numpy_groupies' check_dtype keeps a
+    floating input type, so float32 samples are summed into a float32 ``ret`` (every
+    ``ret[ri] += val`` adds in float64 and rounds back to float32, frei/interp.py:57, 186-202).
+    Default: float64 accumulation (what the GPU path does for either input type).
+    """
+    if keep_dtype and np.asarray(array).dtype == np.float32:
+        return _groupby_bins_agg_f32(np.asarray(array), group, bins, fill_value)
     array = np.asarray(array, dtype=np.float64)
     binned = pd.cut(np.ravel(group), bins)                    # interp.py:284
     codes = np.asarray(binned.codes).astype(np.int64)
@@ -30,6 +38,56 @@ def groupby_bins_agg(array, group, bins, fill_value=0):
         np.add.at(out[r], codes[idx], vals[r])                # ret[ri] += val, interp.py:201-202
     centres = np.array([0.5 * (b.left + b.right) for b in binned.categories])   # interp.py:304-306
     return out.reshape(lead + (n_bins,)), centres
+
+
+def _groupby_bins_agg_f32(array, group, bins, fill_value):
+    binned = pd.cut(np.ravel(group), bins)
+    codes = np.asarray(binned.codes).astype(np.int64)
+    n_bins = binned.categories.size
+    lead = array.shape[:-1]
+    flat = array.reshape(-1, array.shape[-1])
+    out = np.full((flat.shape[0], n_bins), fill_value, dtype=np.float32)
+    for r in range(flat.shape[0]):
+        for i in range(len(codes) - 1):
+            if codes[i] == codes[i + 1]:                      # interp.py:180
+                if codes[i] < 0:
+                    raise ValueError("negative indices not supported")
+                avg_y = np.float64(flat[r, i] + flat[r, i + 1]) / 2          # float32 sum, then / 2
+                out[r, codes[i]] = np.float32(np.float64(out[r, codes[i]]) + avg_y)
+    centres = np.array([0.5 * (b.left + b.right) for b in binned.categories])
+    return out.reshape(lead + (n_bins,)), centres
+
+
+def binned_opacity_exact_one(opacity, wavelength_um, src_T, src_P, temperatures, pressures_bar, wl_bins, lam):
+    """
+    numpy/scipy restatement of one species of binned_opacity's groupies=False branch
+    (frei/opacity.py:150-167 with mapfunc_exact, :29-40): per non-empty pandas.cut bin, nearest
+    (T, P) lookup, np.trapz over the bin's samples divided by their wavelength span, at their
+    mean wavelength; then linear interpolation with extrapolation onto ``lam``.
+    Returns [wavelength, temperature, pressure] (the reference's dimension order).
+    """
+    from scipy.interpolate import interp1d
+    trapz = getattr(np, 'trapezoid', None) or np.trapz
+    wl = np.asarray(wavelength_um, dtype=np.float64)
+    codes = np.asarray(pd.cut(wl, wl_bins).codes)
+    f = interp1d(src_T, np.asarray(opacity, dtype=np.float64), kind='nearest', axis=0,
+                 fill_value='extrapolate', assume_sorted=False)
+    op = f(temperatures)
+    f = interp1d(src_P, op, kind='nearest', axis=1, fill_value='extrapolate', assume_sorted=False)
+    op = f(pressures_bar)                                     # [T', P', n]
+    parts, xs = [], []
+    with np.errstate(invalid='ignore', divide='ignore'):
+        for b in range(len(wl_bins) - 1):
+            idx = np.flatnonzero(codes == b)
+            if idx.size == 0:
+                continue                                      # xarray's groupby skips empty bins
+            w = wl[idx]
+            parts.append(trapz(op[..., idx], w, axis=-1) / (w.max() - w.min()))   # :38-40
+            xs.append(w.mean())
+    binned = np.stack(parts, axis=0)
+    f = interp1d(np.array(xs), binned, kind='linear', axis=0, bounds_error=False,
+                 fill_value='extrapolate', assume_sorted=False)                  # :163-166
+    return f(np.asarray(lam, dtype=np.float64))
 
 
 def binned_opacity_one(opacity, wavelength_um, src_T, src_P, temperatures, pressures_bar, wl_bins):

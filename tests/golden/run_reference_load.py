@@ -111,7 +111,7 @@ def main():
 
     # ---- case H: opacity_dir_to_netcdf on synthetic HELIOS-K .bin files ----
     out['H'] = {}
-    for tag, pressures in (('grid', ['n300', 'p000', 'p100']), ('single_pressure', ['p000'])):
+    for tag, pressures in (('grid', ['n300', 'p000', 'p100']), ('single_pressure', ['p100'])):
         with tempfile.TemporaryDirectory() as tmp:
             d = os.path.join(tmp, '1H2-16O__synthetic')
             os.makedirs(d)

@@ -41,8 +41,17 @@ def plan(request):
     _cabi.check(lib.frei_b200_debug_plan(0))
 
 
-def assert_flux_parity(gpu, ref64, refx):
-    """gpu ~ refx to RTOL_X; gpu ~ ref64 to 1e-6 or 2x the fp64 oracle's own error."""
+HATCH = []           # one record per comparison: how much of it needed the second clause below
+
+
+def assert_flux_parity(gpu, ref64, refx, tag=None):
+    """
+    gpu ~ refx (80-bit evaluation of the reference formulas) to RTOL_X everywhere; gpu ~ ref64 (the
+    reference's own fp64 arithmetic) to 1e-6, or — where the fp64 oracle itself is further than
+    that from its 80-bit self — within 2x the oracle's own error.  Returns how many elements
+    needed that second clause (`n_hatch`), their worst deviation from the fp64 oracle and the
+    levels they sit on, and appends the record to HATCH (dumped to gpurun_out/ at session end).
+    """
     gpu = np.asarray(gpu, dtype=LD)
     ref64 = np.asarray(ref64, dtype=LD)
     refx = np.asarray(refx, dtype=LD)
@@ -51,9 +60,29 @@ def assert_flux_parity(gpu, ref64, refx):
     assert float(ex.max()) < RTOL_X, f'vs extended precision: {float(ex.max()):.3e}'
     e64 = np.abs(gpu - ref64)
     own = np.abs(ref64 - refx)
-    ok = (e64 <= 1e-6 * scale) | (e64 <= 2 * own + 1e-9 * scale)
+    strict = e64 <= 1e-6 * scale
+    ok = strict | (e64 <= 2 * own + 1e-9 * scale)
     assert bool(ok.all()), f'vs fp64 oracle: {float((e64 / scale).max()):.3e}'
-    return float(ex.max()), float((e64 / scale).max())
+    hatch = ~strict
+    rec = dict(tag=tag, n=int(gpu.size), n_hatch=int(hatch.sum()),
+               max_rel_vs_fp64=float((e64 / scale).max()),
+               max_rel_hatch=float((e64 / scale)[hatch].max()) if hatch.any() else 0.0,
+               max_rel_vs_80bit=float(ex.max()),
+               oracle_own_error=float((own / scale).max()),
+               hatch_levels=sorted(set(np.nonzero(hatch)[0].tolist())) if gpu.ndim == 2 else None)
+    HATCH.append(rec)
+    return rec
+
+
+@pytest.fixture(scope='module', autouse=True)
+def _dump_hatch_records():
+    yield
+    import json
+    import os
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), 'gpurun_out')
+    if HATCH and os.path.isdir(out):
+        with open(os.path.join(out, 'parity_hatch.json'), 'w') as fh:
+            json.dump(HATCH, fh, indent=1)
 
 
 def exact_columns_check(w, tabs_cols, cols, sweeps, gpu_states):
@@ -278,8 +307,18 @@ def test_sweeps_match_oracle(L, n_lam, S, f32, plan):
             k += 1
             Fu, Fd = eng.F_up[0].cpu().numpy(), eng.F_down[0].cpu().numpy()
             gpu_states.append((Fu, Fd))
-            assert_flux_parity(Fu, r['Fu'], rx['Fu'])
-            assert_flux_parity(Fd, r['Fd'], rx['Fd'])
+            tag = f'sweeps L={L} n={n_lam} S={S} f32tab={f32} plan={plan} sweep={k - 1}'
+            h_up = assert_flux_parity(Fu, r['Fu'], rx['Fu'], tag + ' F_up')
+            h_dn = assert_flux_parity(Fd, r['Fd'], rx['Fd'], tag + ' F_down')
+            if k > 1:
+                # Only the first emit sweep (zero initial fluxes, optically thin top layers with
+                # delta_tau < 1e-6, where the reference's B'/(2E)(chi - psi - xi) grouping cancels)
+                # needs the second clause; from the first absorb sweep on, the kernel is within the
+                # 1e-6 contract of the reference's own fp64 numbers on every element.
+                assert h_up['n_hatch'] == 0 and h_dn['n_hatch'] == 0, (h_up, h_dn)
+            else:
+                for h in (h_up, h_dn):                  # and there only in the upper atmosphere
+                    assert all(lv >= L // 2 for lv in h['hatch_levels']), h
             for g, x in ((Fu, rx['Fu']), (Fd, rx['Fd'])):
                 e = np.abs(g.astype(LD) - x) / np.maximum(np.abs(x), LD(TINY))
                 worst_x = np.maximum(worst_x, e.max(axis=0).astype(np.float64))
@@ -584,8 +623,11 @@ def test_full_size_sampled_parity_and_integrals():
            lambda a, b: w['mmr'][0], alpha=1, fluxes_up=Fu_r, fluxes_down=Fd_r)
         fn(tabs, T, w['P_bar'], w['lam_um'][idx], F_toa.astype(LD), pl['g'], pl['m_bar'],
            lambda a, b: w['mmr'][0], alpha=1, fluxes_up=Fu_x, fluxes_down=Fd_x, work_dtype=LD)
-        assert_flux_parity(Fu[:, idx], Fu_r, Fu_x)
-        assert_flux_parity(Fd[:, idx], Fd_r, Fd_x)
+        name = 'emit' if direction == FREI_EMIT else 'absorb'
+        h_up = assert_flux_parity(Fu[:, idx], Fu_r, Fu_x, f'C2 full size, 3000 sampled bins, {name} F_up')
+        h_dn = assert_flux_parity(Fd[:, idx], Fd_r, Fd_x, f'C2 full size, 3000 sampled bins, {name} F_down')
+        if direction == FREI_ABSORB:        # the 1e-6 contract holds element-wise from the first absorb on
+            assert h_up['n_hatch'] == 0 and h_dn['n_hatch'] == 0, (h_up, h_dn)
         # integrals: F1_up of step i is fluxes_up[i] (before the sweep for absorb / carried
         # for emit), F1_down = fluxes_down[i] after the sweep.
         sums = eng.sums[0].cpu().numpy()
@@ -862,3 +904,85 @@ def test_split_reduce_update_sequence_equals_fused_post(plan):
             for name in ('T', 'dT', 'sums', 'F_up', 'F_down'):
                 a, b = getattr(fused, name).cpu().numpy(), getattr(split, name).cpu().numpy()
                 np.testing.assert_allclose(b, a, rtol=1e-12, atol=1e-300, err_msg=f'{name}, iteration {it}')
+
+
+@pytest.mark.parametrize('L,n_lam,S,force', [(100, 2050, 8, 2), (100, 2050, 8, 3), (200, 3002, 3, 2),
+                                             (200, 3002, 3, 3), (256, 514, 1, 2)])
+def test_large_shapes_match_oracle(L, n_lam, S, force):
+    """
+    The layer counts and species counts of BASELINE configs C3 (100 layers, 8 species) and C5
+    (200 layers) and the largest layer count the reduction supports (256), at a few thousand
+    wavelengths, with 64-wide chunks (force 2) and the mixed plan (force 3): one emit + absorb
+    iteration against the fp64 and 80-bit oracle.
+    """
+    from frei_b200 import synthetic, _cabi
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB
+    lib = _cabi.load()
+    _cabi.check(lib.frei_b200_debug_plan(force))
+    try:
+        w = synthetic.make_workload(L, n_lam, S, 3200.0 if S == 8 else 2400.0)
+        tabs = synthetic.host_tables(w)
+        ref = _oracle_iteration(w, tabs, 1)
+        refx = _oracle_iteration(w, tabs, 1, wd=LD)
+        eng = _engine(w)
+        for k, direction in enumerate((FREI_EMIT, FREI_ABSORB)):
+            eng.sweep(direction, with_dtaus=True)
+            Fu, Fd = eng.F_up[0].cpu().numpy(), eng.F_down[0].cpu().numpy()
+            tag = f'large L={L} n={n_lam} S={S} plan={force} sweep={k}'
+            assert_flux_parity(Fu, ref[k]['Fu'], refx[k]['Fu'], tag + ' F_up')
+            assert_flux_parity(Fd, ref[k]['Fd'], refx[k]['Fd'], tag + ' F_down')
+            assert _rel(eng.dtaus[0].cpu().numpy(), ref[k]['dtaus']).max() < 1e-12
+            sums = eng.sums[0].cpu().numpy()
+            lo, hi = (1, L) if direction == FREI_EMIT else (0, L - 1)
+            assert _rel(sums[lo:hi], refx[k]['bol'][lo:hi]).max() < 1e-10
+            np.testing.assert_allclose(eng.dT[0].cpu().numpy(), ref[k]['dT'], rtol=1e-6, atol=1e-8)
+            np.testing.assert_allclose(eng.T[0].cpu().numpy(), ref[k]['T'], rtol=0, atol=1e-6)
+    finally:
+        _cabi.check(lib.frei_b200_debug_plan(0))
+
+
+def test_c4_shaped_batch_against_per_atmosphere_oracle():
+    """
+    A C4-shaped batch (T_eq x log g x metallicity grid, here 8 x 8 x 4 = 256 atmospheres, 20 layers
+    x 192 bins) solved with the device-side convergence rule.  A spread sample of atmospheres is
+    solved one by one with the oracle's Grid.emission_spectrum: same iteration count, T within
+    1e-3 K, spectrum within 1e-6.  The cold, metal-rich corner diverges in the reference's explicit
+    scheme (T < 0, then NaN): there the rule must still stop the atmosphere — np.sign(nan) !=
+    np.sign(nan) counts as a zero crossing in frei/core.py:306-311 — and both end with NaN.
+    """
+    from frei_b200 import synthetic
+    from frei_b200.engine import Engine, FREI_F64
+    L, n_lam, S = 20, 192, 3
+    w = synthetic.make_workload(L, n_lam, S)
+    tab = synthetic.device_table(w, FREI_F64)
+    tabs = synthetic.host_tables(w)
+    pl = w['planet']
+    tt, gg, mm = [x.ravel() for x in np.meshgrid(np.linspace(1000, 2500, 8), np.linspace(2.5, 4.0, 8),
+                                                 np.linspace(-1, 2, 4), indexing='ij')]
+    B = tt.size
+    T0 = tt[:, None] * (w['P_bar'][None, :] / 0.1) ** 0.1
+    mmr = w['mmr'][None] * (10.0 ** mm)[:, None, None]
+    eng = Engine(tab, w['lam_um'], np.broadcast_to(w['P_bar'], (B, L)), T0, mmr, g=10.0 ** gg,
+                 m_bar=pl['m_bar'], alpha=1.0, T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+                 ftoa_scale=(tt / 2400.0) ** 4)
+    cap = 300
+    iters, T = eng.solve_batch(cap, check_every=5)
+    spec = eng.F_up[:, L - 1, :].cpu().numpy()
+    assert (iters < cap).all(), f'{(iters >= cap).sum()} atmospheres were stopped by the cap'
+    finite = np.isfinite(T).all(axis=1)
+    sample = sorted(set(np.linspace(0, B - 1, 14).astype(int).tolist() + np.flatnonzero(~finite)[:3].tolist()))
+    n_nan = 0
+    for b in sample:
+        planet = dict(pl, g=10.0 ** gg[b], a_rstar=pl['a_rstar'] / (tt[b] / 2400.0) ** 2)
+        with np.errstate(all='ignore'):
+            s_ref, T_ref, hist, dtaus, n_it = O.emission_spectrum(
+                tabs, T0[b], w['P_bar'], w['lam_um'], planet, lambda x, y, m=mmr[b, 0]: m, n_timesteps=cap)
+        if np.isfinite(T_ref).all():
+            assert finite[b] and iters[b] == n_it, (b, iters[b], n_it)
+            assert np.abs(T[b] - T_ref).max() < 1e-3
+            assert _rel(spec[b], s_ref).max() < 1e-6
+        else:
+            n_nan += 1
+            assert not finite[b], b                        # diverged on both sides ...
+            assert n_it < 12 and iters[b] < 12, (b, iters[b], n_it)   # ... and stopped by the rule at once
+    assert n_nan >= 1 or finite.all()
