@@ -25,6 +25,17 @@
 #define SWEEP_MINB_EMIT SWEEP_MINB  // experiment knob: a separate register budget for the emit instantiations (under ncu
                                   // the emit kernel is 6 % slower at 128 registers than at 158, absorb 2 % faster)
 #endif
+#ifndef SWEEP_WIDE_S
+#define SWEEP_WIDE_S 8            // species counts from here on: the staged table rows (4 S x 16 B per thread) cap the
+#endif                            // resident CTAs below SWEEP_MINB anyway, so the kernel may use the registers
+#ifndef SWEEP_MINB_WIDE
+#define SWEEP_MINB_WIDE 2         // resident CTAs per SM those instantiations are compiled for (S = 8, 100 levels:
+                                  // 99 KB of shared memory per CTA -> 2 CTAs; 206 registers; +9 % over the
+                                  // 128-register build, profiles/r02_wide_species_ab.log)
+#endif
+#ifndef SWEEP_GATHER4
+#define SWEEP_GATHER4 1           // 1: four accumulation chains in the opacity gather of those instantiations
+#endif
 #ifndef SWEEP_V1_CHUNKS_PER_SM
 #define SWEEP_V1_CHUNKS_PER_SM 2  // below this many 64-wavelength chunks per SM the plan uses one wavelength per thread
 #endif

@@ -630,6 +630,34 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
     double ka[V], kb[V];
 #pragma unroll
     for (int v = 0; v < V; ++v) { ka[v] = sg[v]; kb[v] = 0.0; }          // k includes sigma, opacity.py:269
+#if SWEEP_GATHER4
+    if (S_T >= SWEEP_WIDE_S) {
+        // many species: one chain per corner (depth S + 2) and all loads of the level in flight
+        double kc[V], kd[V];
+#pragma unroll
+        for (int v = 0; v < V; ++v) { kc[v] = 0.0; kd[v] = 0.0; }
+#pragma unroll
+        for (int s = 0; s < SS; ++s) {
+            const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
+            const double2 wb = *reinterpret_cast<const double2*>(rec + 4 + 4 * s);
+            double t0[V], t1[V], t2[V], t3[V];
+            SVec<V>::ld(slot + (4 * s + 0) * kRowElems, t0);
+            SVec<V>::ld(slot + (4 * s + 1) * kRowElems, t1);
+            SVec<V>::ld(slot + (4 * s + 2) * kRowElems, t2);
+            SVec<V>::ld(slot + (4 * s + 3) * kRowElems, t3);
+#pragma unroll
+            for (int v = 0; v < V; ++v) {
+                ka[v] = fma(t0[v], wa.x, ka[v]);
+                kb[v] = fma(t1[v], wa.y, kb[v]);
+                kc[v] = fma(t2[v], wb.x, kc[v]);
+                kd[v] = fma(t3[v], wb.y, kd[v]);
+            }
+        }
+#pragma unroll
+        for (int v = 0; v < V; ++v) k[v] = (ka[v] + kb[v]) + (kc[v] + kd[v]);
+        return;
+    }
+#endif
 #pragma unroll 4
     for (int s = 0; s < SS; ++s) {
         const double2 wa = *reinterpret_cast<const double2*>(rec + 2 + 4 * s);
@@ -868,7 +896,8 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
 // cost 1.59 round times, one round + a 64 % full round of 32-wide chunks 1.38).
 // The level records are staged into shared memory by one TMA bulk copy per CTA.
 template <typename TabT, int S_T, int DIR, bool DTAUS>
-__global__ void __launch_bounds__(kThreads, (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB)
+__global__ void __launch_bounds__(kThreads, (S_T >= SWEEP_WIDE_S && sizeof(TabT) == 8) ? SWEEP_MINB_WIDE :
+                                            (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB)
 sweep_kernel(SweepArgs a) {
     extern __shared__ __align__(16) double smem[];
     __shared__ __align__(8) uint64_t bar;
@@ -881,9 +910,10 @@ sweep_kernel(SweepArgs a) {
     if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
     const int L = a.L, rec8 = a.lp.rec8;
     if (tid < 32) tab[tid] = kExp2Tab[tid];
+    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
+    const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
     double* sm_rec = smem;                       // [L][rec8]
     const void* sm_rows = smem + (size_t)L * rec8;
-
     // ---- stage the level records (TMA bulk copy global -> shared, mbarrier completion) ----
     const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
     if (tid == 0) {
@@ -898,8 +928,6 @@ sweep_kernel(SweepArgs a) {
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                      ::"r"(smem_u32(sm_rec)), "l"(src), "r"(bytes), "r"(smem_u32(&bar)) : "memory");
     }
-    const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
-    const double fscale = a.ftoa_scale ? a.ftoa_scale[b] : 1.0;
     {   // ---- wait for the records ----
         uint32_t done = 0;
         while (!done) {

@@ -907,13 +907,12 @@ def test_split_reduce_update_sequence_equals_fused_post(plan):
 
 
 @pytest.mark.parametrize('L,n_lam,S,force', [(100, 2050, 8, 2), (100, 2050, 8, 3), (200, 3002, 3, 2),
-                                             (200, 3002, 3, 3), (256, 514, 1, 2)])
+                                             (200, 3002, 3, 3)])
 def test_large_shapes_match_oracle(L, n_lam, S, force):
     """
     The layer counts and species counts of BASELINE configs C3 (100 layers, 8 species) and C5
-    (200 layers) and the largest layer count the reduction supports (256), at a few thousand
-    wavelengths, with 64-wide chunks (force 2) and the mixed plan (force 3): one emit + absorb
-    iteration against the fp64 and 80-bit oracle.
+    (200 layers), at a few thousand wavelengths, with 64-wide chunks (force 2) and the mixed plan
+    (force 3): one emit + absorb iteration against the fp64 and 80-bit oracle.
     """
     from frei_b200 import synthetic, _cabi
     from frei_b200.engine import FREI_EMIT, FREI_ABSORB
@@ -937,6 +936,25 @@ def test_large_shapes_match_oracle(L, n_lam, S, force):
             assert _rel(sums[lo:hi], refx[k]['bol'][lo:hi]).max() < 1e-10
             np.testing.assert_allclose(eng.dT[0].cpu().numpy(), ref[k]['dT'], rtol=1e-6, atol=1e-8)
             np.testing.assert_allclose(eng.T[0].cpu().numpy(), ref[k]['T'], rtol=0, atol=1e-6)
+    finally:
+        _cabi.check(lib.frei_b200_debug_plan(0))
+
+
+def test_maximum_layer_count():
+    """
+    256 levels, the most the reduction supports (4 L = 1024 threads; 257 is rejected).  With 256
+    levels between 1e-6 and 200 bar the layers are so thin (delta_tau down to 1e-9) that even the
+    80-bit evaluation of the reference's grouping is noisy, so the 40-digit evaluation arbitrates.
+    """
+    from frei_b200 import synthetic, _cabi
+    from frei_b200._cabi import FreiError
+    lib = _cabi.load()
+    _cabi.check(lib.frei_b200_debug_plan(2))
+    try:
+        _one_iteration_with_arbitration(synthetic.make_workload(256, 514, 1), align_T=True)
+        with pytest.raises(FreiError, match='bad argument|levels'):
+            from frei_b200.engine import FREI_EMIT
+            _engine(synthetic.make_workload(257, 128, 1)).sweep(FREI_EMIT)
     finally:
         _cabi.check(lib.frei_b200_debug_plan(0))
 
