@@ -47,13 +47,22 @@ WORKLOADS = {
 }
 
 
-def read_traffic(workload, table_dtype, flux_dtype, world):
-    """DRAM bytes per sweep launch from the committed ncu capture of this workload (or None)."""
+def read_traffic(workload, table_dtype, flux_dtype, world, evals=None):
+    """
+    DRAM bytes per sweep launch from the committed ncu capture of this workload (or None).  With
+    `evals` (evaluations of the launch in question) the captured bytes are scaled per evaluation,
+    so the C3 entry, captured on one of eight shards, also serves the other shard sizes.
+    """
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             d = json.load(fh)
         e = d.get(f'{workload}_tab{table_dtype}_flux{flux_dtype}_n{world}')
-        return (e['bytes_per_launch'], e['source']) if e else (None, None)
+        if not e:
+            return None, None
+        b = e['bytes_per_launch']
+        if evals and e.get('evals_per_launch'):
+            b = b * evals / e['evals_per_launch']
+        return b, e['source']
     except (OSError, ValueError, KeyError):
         return None, None
 
@@ -184,13 +193,13 @@ def run_reference(args):
 FALLBACK_OPS_PER_EVAL = {'dfma': 55.0, 'dmul': 33.1, 'dadd': 20.4}
 
 
-def read_fp64_ops(workload, table_dtype, flux_dtype, evals_per_launch_captured):
+def read_fp64_ops(workload, table_dtype, flux_dtype):
     """fp64 thread instructions per evaluation from the committed ncu capture of this workload."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'traffic.json')) as fh:
             e = json.load(fh)[f'{workload}_tab{table_dtype}_flux{flux_dtype}_n1']
-        ops = e['fp64_thread_ops_per_launch']
-        return {k: ops[k] / evals_per_launch_captured for k in ('dfma', 'dmul', 'dadd')}, e['source']
+        ops, n = e['fp64_thread_ops_per_launch'], e['evals_per_launch']
+        return {k: ops[k] / n for k in ('dfma', 'dmul', 'dadd')}, e['source']
     except (OSError, ValueError, KeyError):
         return None, None
 
@@ -308,9 +317,10 @@ def fp64_peak(dev):
     return out.value
 
 
-def roofline_of(r, args, tdtype, fdtype, world, dev):
-    """Roofline of the sweep kernel of run `r` against the resource that binds it."""
+def roofline_of(r, workload, tdtype, fdtype, dev):
+    """Roofline of the sweep kernel of run `r` (workload name `workload`) against the resource that binds it."""
     from frei_b200.engine import FREI_F32
+    tbits, fbits = (32 if tdtype == FREI_F32 else 64), (32 if fdtype == FREI_F32 else 64)
     L, S, n_loc = r['L'], r['S'], r['hi'] - r['lo']
     b_tab = 4 if tdtype == FREI_F32 else 8
     b_flux = 4 if fdtype == FREI_F32 else 8
@@ -319,7 +329,7 @@ def roofline_of(r, args, tdtype, fdtype, world, dev):
     peak_hbm, peak_src = read_peaks()
     algo_bytes = evals * (4 * S * b_tab + 3 * b_flux)
     reuse_bytes = evals * 3 * b_flux + distinct_table_rows(r['w'], S) * n_loc * b_tab
-    traffic, traffic_src = read_traffic(args.workload, args.table_dtype, args.flux_dtype, 1)
+    traffic, traffic_src = read_traffic(workload, tbits, fbits, 1, evals)
     hbm = {'peak': peak_hbm, 'peak_source': peak_src, 'unit': 'GB/s',
            'algorithmic_bytes': algo_bytes, 'algorithmic_gbs': algo_bytes / t / 1e9,
            'reuse_aware_bytes': reuse_bytes, 'reuse_aware_gbs': reuse_bytes / t / 1e9,
@@ -341,8 +351,7 @@ def roofline_of(r, args, tdtype, fdtype, world, dev):
                          'time (the SURVEY 8d algorithmic bytes would count table rows that never leave '
                          'the chip: see hbm.algorithmic_gbs)')
     # fp64 arithmetic: the fp64 pipe binds (ncu: 45 % pipe-active vs 42 % of HBM on real traffic)
-    ops, ops_src = read_fp64_ops(args.workload, args.table_dtype, args.flux_dtype,
-                                 (WORKLOADS[args.workload][0] - 1) * WORKLOADS[args.workload][1])
+    ops, ops_src = read_fp64_ops(workload, tbits, fbits)
     if ops is None:
         ops, ops_src = FALLBACK_OPS_PER_EVAL, 'fallback: counts of the committed C2 capture (S = 3)'
     dfma_peak = fp64_peak(dev)                                             # thread DFMA/s, measured now
@@ -435,7 +444,7 @@ def run_ours(args):
     r = time_sweeps(args, args.workload, world, rank, dev, group, tdtype, fdtype, args.steps, args.warmup,
                     sample_clocks=True, local_rank=local_rank)
     L, S, lo, hi = r['L'], r['S'], r['lo'], r['hi']
-    roof = roofline_of(r, args, tdtype, fdtype, world, dev)
+    roof = roofline_of(r, args.workload, tdtype, fdtype, dev)
     e2e = run_e2e(args, r, world, rank, dev, group, fdtype)
     if e2e.get('value'):
         e2e['frac_of_device_rate'] = e2e['value'] / r['value']
@@ -458,7 +467,7 @@ def run_ours(args):
                 'ms_per_step': c3['ms'] / c3['steps'], 'steps': c3['steps'], 'warmup': c3['warmup'],
                 'kernel_avg_ms': c3['sweep_avg_ms'], 'n_gpus': world, 'collective': c3['collective'],
                 'workload': WORKLOADS['C3'][5], 'n_layers': c3['L'], 'n_lambda_global': c3['n_lam_global'],
-                'n_species': c3['S'], 'dtype': 'f64'}
+                'n_species': c3['S'], 'dtype': 'f64', 'roofline': roofline_of(c3, 'C3', FREI_F64, FREI_F64, dev)}
             c3 = None
             torch.cuda.empty_cache()
         except Exception as exc:                               # pragma: no cover
@@ -466,12 +475,11 @@ def run_ours(args):
         try:
             f32 = time_sweeps(args, 'C2', world, rank, dev, group, FREI_F32, FREI_F32, steps=args.steps,
                               warmup=3)
-            a32 = argparse.Namespace(**dict(vars(args), table_dtype=32, flux_dtype=32))
             extras['fp32_c2'] = {
                 'metric': METRIC, 'value': f32['value'], 'unit': UNIT, 'scaling': f32['scaling'],
                 'ms_per_step': f32['ms'] / f32['steps'], 'dtype': 'f32', 'n_gpus': world,
                 'note': 'fp32 table, flux state and arithmetic, fp64 wavelength integrals (contract 1e-4)',
-                'roofline': roofline_of(f32, a32, FREI_F32, FREI_F32, world, dev)}
+                'roofline': roofline_of(f32, 'C2', FREI_F32, FREI_F32, dev)}
             f32 = None
             torch.cuda.empty_cache()
         except Exception as exc:                               # pragma: no cover

@@ -7,7 +7,7 @@ import sys
 
 OURS = ('sweep_kernel', 'sweep_f32_kernel', 'post_kernel', 'prep_kernel', 'spectral_kernel',
         'update_prep_kernel', 'kappa_kernel', 'propagate_kernel', 'diag_kernel', 'diag_finish_kernel',
-        'bin_trapz')
+        'bin_trapz', 'regrid_kernel')   # dfma_peak_kernel is the roofline's own measurement, not the path
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
 hdr = rows[0]
 iname, ival = hdr.index('Kernel Name'), hdr.index('Metric Value')
@@ -21,7 +21,7 @@ ours = {k: v for k, v in agg.items() if any(o in k for o in OURS)}
 tot = sum(v[1] for v in ours.values())
 out = {
     'command': 'ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv python bench.py '
-               '--steps 2 --warmup 3 --no-cpu-baseline',
+               '--steps 2 --warmup 3 --no-extras --no-cpu-baseline',
     'note': 'cold-cache, serialised launches: compare shares, not absolutes; the list also holds the '
             'torch kernels of table generation and the e2e leg',
     'share_of_frei_b200_kernels': {

@@ -1,5 +1,6 @@
 """Summarise an `ncu --set full` report of the sweep kernel into profiles/ (run where ncu is installed).
-usage: python scripts/ncu_summary.py REPORT.ncu-rep CAPTURE_TAG "what was captured" [--write [KEY]]
+usage: python scripts/ncu_summary.py REPORT.ncu-rep CAPTURE_TAG "what was captured" [--write [KEY [EVALS]]]
+(EVALS = evaluations per captured launch, (L - 1) x n_lambda: lets bench.py scale the entry to its own launch size)
 Prints one JSON object per captured launch; --write appends them to
 profiles/r02_sweep_kernel_ncu_summary.json and refreshes the entry KEY (default C2_tab64_flux64_n1)
 of profiles/traffic.json: DRAM bytes and executed fp64 thread operations per launch, which
@@ -70,6 +71,7 @@ def main():
         allc = (json.load(open(p)) if os.path.exists(p) else []) + res
         wi = sys.argv.index('--write')
         key = sys.argv[wi + 1] if len(sys.argv) > wi + 1 else 'C2_tab64_flux64_n1'
+        evals = int(sys.argv[wi + 2]) if len(sys.argv) > wi + 2 else None
         json.dump(allc, open(p, 'w'), indent=1)
         if traffic:
             tp = os.path.join(ROOT, 'profiles', 'traffic.json')
@@ -79,6 +81,8 @@ def main():
                 'per_launch': traffic,
                 'source': f'profiles/r02_sweep_kernel_ncu_summary.json capture {tag} '
                           f'(ncu --set full of scripts/prof_sweep.py)'}
+            if evals:
+                t[key]['evals_per_launch'] = evals
             if ops:      # thread-level fp64 instructions per launch (DFMA = 2 flops, DMUL / DADD = 1)
                 t[key]['fp64_thread_ops_per_launch'] = {
                     k: sum(o[k] for o in ops) / len(ops) for k in ('dfma', 'dmul', 'dadd')}
