@@ -40,7 +40,11 @@
 #define SWEEP_V1_CHUNKS_PER_SM 2  // below this many 64-wavelength chunks per SM the plan uses one wavelength per thread
 #endif
 #ifndef SWEEP_MIXED_TAIL
-#define SWEEP_MIXED_TAIL 1        // 1: a last round of chunks that is at most half full runs 32-wide chunks
+#define SWEEP_MIXED_TAIL 0        // 1: a last round of chunks that is at most half full runs 32-wide chunks (round-2
+                                  // experiment: no gain at any size; the relay plan replaces it)
+#endif
+#ifndef SWEEP_RELAY
+#define SWEEP_RELAY 1             // 1: relay plan for single atmospheres with more 64-wide chunks than resident warps
 #endif
 #ifndef SWEEP_E_VOTE
 #define SWEEP_E_VOTE 1            // 1: warp vote selects the E = 1 specialisation of the layer step
@@ -84,6 +88,11 @@ struct SweepArgs {
     int n2;                     // fp64 kernel: chunks [0, n2) are 64 wavelengths wide, [n2, rows) 32 wide
     int32_t* plan_hdr;          // workspace header: [0] = rows, written by the sweep, read by post_kernel
     int B, L, S, N_T;
+    // relay plan (fp64 kernel, single atmosphere, more chunks than resident warps): the (chunk, layer-step)
+    // pairs are dealt out in equal runs of relay_quota steps per resident warp, 0 = every warp keeps
+    // whole chunks; relay_flags[chunk] hands a chunk cut by a run boundary from one warp to the next
+    int relay_quota;
+    unsigned int* relay_flags;  // [rows], zero between launches
 };
 
 // Sum four per-lane values across the warp; on return lanes 0, 8, 16, 24 hold the

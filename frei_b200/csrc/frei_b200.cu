@@ -90,7 +90,7 @@ static inline LayerParams layer_params_view(void* p, int S) {
 }
 static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
 static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + 2 * kWarps; }   // bound on the plan's rows
-// ws->partials: [B][rows_max][L][4] chunk rows | [B][kPostChunks][L][4] stage-1 sums | [B] tickets | header
+// ws->partials: [B][rows_max][L][4] chunk rows | [B][kPostChunks][L][4] stage-1 sums | [B] tickets | header | [rows_max] relay flags
 static inline double* ws_chunk_sums(const frei_workspace* ws, int B, int L, int64_t n_lam) {
     return ws->partials + (int64_t)B * sweep_rows_max(n_lam) * L * 4;
 }
@@ -99,6 +99,10 @@ static inline unsigned int* ws_counters(const frei_workspace* ws, int B, int L, 
 }
 static inline int32_t* ws_plan_hdr(const frei_workspace* ws, int B, int L, int64_t n_lam) {
     return reinterpret_cast<int32_t*>(reinterpret_cast<char*>(ws_counters(ws, B, L, n_lam)) + round16((int64_t)B * 4));
+}
+// relay flags, one per chunk row of a single atmosphere (zero between launches)
+static inline unsigned int* ws_relay_flags(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return reinterpret_cast<unsigned int*>(ws_plan_hdr(ws, B, L, n_lam) + 4);
 }
 
 // ---------------------------------------------------------------------------
@@ -631,7 +635,7 @@ __device__ __forceinline__ void gather_smem(const TabT* slot, const double* rec,
 #pragma unroll
     for (int v = 0; v < V; ++v) { ka[v] = sg[v]; kb[v] = 0.0; }          // k includes sigma, opacity.py:269
 #if SWEEP_GATHER4
-    if (S_T >= SWEEP_WIDE_S) {
+    if (S_T >= SWEEP_WIDE_S && sizeof(TabT) == 8) {      // the instantiations compiled for SWEEP_MINB_WIDE CTAs/SM
         // many species: one chain per corner (depth S + 2) and all loads of the level in flight
         double kc[V], kd[V];
 #pragma unroll
@@ -752,12 +756,45 @@ __device__ __forceinline__ void layer_step(Lane<V>& t, const double* k, double d
 // written back.  The layer loop body is a single basic block (no data-dependent or uniform
 // branches) and there is no CTA barrier: warps run their chunks independently.
 // `jbase` = first wavelength of the chunk, `part` = its [L][4] row of wavelength-integral partials.
-template <typename TabT, int S_T, int DIR, int V, bool DTAUS>
+// A chunk cut by the relay plan is handed from the warp that ran its first layer-steps to the warp that
+// runs the rest through the flux arrays themselves (the carried stream of step s is the row step
+// s - 1 stored) and one flag per chunk: stores -> warp barrier -> st.release by lane 0 on one side,
+// ld.acquire spin by lane 0 -> warp barrier on the other.  The receiver puts the flag back to 0, so a
+// launch leaves the flags as it found them (CUDA graphs replay the same arguments).  The sender is
+// always a warp with a lower index in the same or the previous CTA and runs its piece first; the
+// receiver runs its piece last, at least relay_quota - (L - 1) layer-steps later.  A wait that runs
+// out (a lost sender: never seen) poisons the chunk's integrals so that the solve fails loudly.
+__device__ __forceinline__ bool relay_wait(unsigned int* flag, int lane) {
+    unsigned int ok = 1;
+    if (lane == 0) {
+        unsigned int v = 0;
+#pragma unroll 1
+        for (int spin = 0; spin < (1 << 22); ++spin) {
+            asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+            if (v) break;
+            __nanosleep(64);
+        }
+        ok = v;
+        asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(0u) : "memory");
+    }
+    __syncwarp();
+    return __shfl_sync(0xffffffffu, ok, 0) != 0;
+}
+__device__ __forceinline__ void relay_signal(unsigned int* flag, int lane) {
+    __syncwarp();
+    if (lane == 0) asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(1u) : "memory");
+}
+
+// PIECES = false: all L - 1 layer-steps of the chunk (s0, s1, flag ignored); true: steps [s0, s1) in
+// visiting order (emit: level 1 + s, absorb: level L - 2 - s), `flag` = the chunk's relay flag.
+template <typename TabT, int S_T, int DIR, int V, bool DTAUS, bool PIECES>
 __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t jbase, double* part,
                                             const double* sm_rec, const void* sm_rows, const double* tab,
-                                            double sscale, double fscale) {
+                                            double sscale, double fscale, int s0, int s1,
+                                            unsigned int* flag) {
     const int tid = threadIdx.x, lane = tid & 31;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
+    if (!PIECES) { s0 = 0; s1 = L - 1; }
     const int SS = (S_T > 0) ? S_T : S;
     const int64_t n_lam = a.n_lam;
     const int64_t rowT = (int64_t)a.N_T * n_lam;
@@ -784,7 +821,7 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
         if (!live) t.wj[v] = 0.0;
         t.thr[v] = __double2hiint(t.sg[v] * 9.00003433227539062) + 1;    // 9 (1 + 2^-18)
     }
-    if (DTAUS && live) {                         // leading row of ones, twostream.py:352/:487
+    if (DTAUS && live && s0 == 0) {              // leading row of ones, twostream.py:352/:487
         double one[V];
 #pragma unroll
         for (int v = 0; v < V; ++v) one[v] = 1.0;
@@ -798,22 +835,27 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
     };
     if (DIR == FREI_EMIT) {
         // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
-        const double* rec = sm_rec + rec8;
-        const double* pFd = Fd + 2 * n_lam;                              // fluxes_down[i + 1]
-        if (L > 2) {
+        const int i0 = 1 + s0, iE = min(1 + s1, L - 1);                  // regular layers [i0, iE) of this piece
+        const double* rec = sm_rec + (size_t)i0 * rec8;
+        const double* pFd = Fd + (int64_t)(i0 + 1) * n_lam;              // fluxes_down[i + 1]
+        if (i0 < L - 1) {
             Vec<V>::ld(pFd, nxt);
         }
         stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
-        Vec<V>::ld(Fu + n_lam, t.Fcar);                                  // fluxes_up[1], stale
+        if (PIECES && s0 > 0 && !relay_wait(flag, lane)) {               // lost sender: NaN integrals, the solve fails loudly
+#pragma unroll
+            for (int v = 0; v < V; ++v) t.wj[v] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        Vec<V>::ld(Fu + (int64_t)i0 * n_lam, t.Fcar);                    // fluxes_up[i0]: stale (i0 = 1) or handed over
         const double invT1 = rec[1];
 #pragma unroll
         for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invT1, tab);
-        double* pFu_out = Fu + 2 * n_lam;                                // fluxes_up[i + 1]
-        double* pFd_out = Fd + n_lam;                                    // fluxes_down[i]
-        double* pdt = DTAUS ? dt_out + n_lam : nullptr;
+        double* pFu_out = Fu + (int64_t)(i0 + 1) * n_lam;                // fluxes_up[i + 1]
+        double* pFd_out = Fd + (int64_t)i0 * n_lam;                      // fluxes_down[i]
+        double* pdt = DTAUS ? dt_out + (int64_t)i0 * n_lam : nullptr;
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
-        for (int i = 1; i < L - 1; ++i) {
+        for (int i = i0; i < iE; ++i) {
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];                 // fluxes_down[i + 1]
             pFd += n_lam;
@@ -832,7 +874,8 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
             cp_async_wait_all();
             gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
         }
-        {   // top: p_2 extrapolated (in the record), T_2 = T_1, F_2_down = F_TOA, F_2_up discarded
+        if (!PIECES || s1 == L - 1) {
+            // top: p_2 extrapolated (in the record), T_2 = T_1, F_2_down = F_TOA, F_2_up discarded
             Vec<V>::ldg(a.f_toa + j, oth);                               // :379-382
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] *= fscale;
@@ -843,22 +886,27 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
             }
             publish(red, L - 1);
         }
-        if (lane < 4) part[lane] = 0.0;                    // level 0 is not visited
+        if (s0 == 0 && lane < 4) part[lane] = 0.0;         // level 0 is not visited
     } else {
-        const double* rec = sm_rec + (size_t)(L - 2) * rec8;
-        const double* pFu = Fu + (int64_t)(L - 2) * n_lam;               // fluxes_up[i], stale
+        const int i0 = L - 2 - s0, iE = L - 1 - s1;                      // layers i0 down to iE of this piece
+        const double* rec = sm_rec + (size_t)i0 * rec8;
+        const double* pFu = Fu + (int64_t)i0 * n_lam;                    // fluxes_up[i], stale
         Vec<V>::ld(pFu, nxt);
         stage_rows<TabT, S_T, V>(tabj, rec, S, n_lam, rowT, stage);      // commits the group
-        Vec<V>::ld(Fd + (int64_t)(L - 1) * n_lam, t.Fcar);               // fluxes_down[L-1]
+        if (PIECES && s0 > 0 && !relay_wait(flag, lane)) {
+#pragma unroll
+            for (int v = 0; v < V; ++v) t.wj[v] = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        Vec<V>::ld(Fd + (int64_t)(i0 + 1) * n_lam, t.Fcar);              // fluxes_down[i0 + 1]: stale (top) or handed over
         const double invTt = rec[rec8 + 1];
 #pragma unroll
         for (int v = 0; v < V; ++v) t.Bcar[v] = planck(t.c1[v], t.c2[v], invTt, tab);
-        double* pFu_out = Fu + (int64_t)(L - 1) * n_lam;                 // fluxes_up[i + 1]
-        double* pFd_out = Fd + (int64_t)(L - 2) * n_lam;                 // fluxes_down[i]
-        double* pdt = DTAUS ? dt_out + n_lam : nullptr;                  // visiting order
+        double* pFu_out = Fu + (int64_t)(i0 + 1) * n_lam;                // fluxes_up[i + 1]
+        double* pFd_out = Fd + (int64_t)i0 * n_lam;                      // fluxes_down[i]
+        double* pdt = DTAUS ? dt_out + (int64_t)(1 + s0) * n_lam : nullptr;   // visiting order
         cp_async_wait_all();
         gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
-        for (int i = L - 2; i >= 0; --i) {
+        for (int i = i0; i >= iE; --i) {
 #pragma unroll
             for (int v = 0; v < V; ++v) oth[v] = nxt[v];                 // fluxes_up[i], :512
             pFu -= n_lam;
@@ -880,8 +928,9 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
                 gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
             }
         }
-        if (lane < 4) part[(L - 1) * 4 + lane] = 0.0;               // level L-1 is not visited
+        if (s0 == 0 && lane < 4) part[(L - 1) * 4 + lane] = 0.0;    // level L-1 is not visited
     }
+    if (PIECES && s1 < L - 1) relay_signal(flag, lane);    // the rest of the chunk belongs to another warp
 }
 
 // The sweep kernel.  The wavelength axis is cut into a.n2 chunks of 64 wavelengths (two per thread)
@@ -895,7 +944,7 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
 // instructions per layer — which shortens the tail of the launch (C2: 1.32 rounds of 64-wide chunks
 // cost 1.59 round times, one round + a 64 % full round of 32-wide chunks 1.38).
 // The level records are staged into shared memory by one TMA bulk copy per CTA.
-template <typename TabT, int S_T, int DIR, bool DTAUS>
+template <typename TabT, int S_T, int DIR, bool DTAUS, bool RELAY>
 __global__ void __launch_bounds__(kThreads, (S_T >= SWEEP_WIDE_S && sizeof(TabT) == 8) ? SWEEP_MINB_WIDE :
                                             (DIR == FREI_EMIT) ? SWEEP_MINB_EMIT : SWEEP_MINB)
 sweep_kernel(SweepArgs a) {
@@ -938,14 +987,41 @@ sweep_kernel(SweepArgs a) {
         }
     }
 
-    const int G = gridDim.x;
-    for (int q = warp * G + blockIdx.x; q < a.rows; q += kWarps * G) {
-        double* part = a.partials + ((int64_t)b * a.rows + q) * L * 4;
-        if (q < a.n2)
-            sweep_chunk<TabT, S_T, DIR, 2, DTAUS>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale, fscale);
+    const int G = gridDim.x, NS = L - 1;
+    if (!RELAY) {
+        // whole chunks q = w G + c, + kWarps G, ...
+        for (int q = warp * G + blockIdx.x; q < a.rows; q += kWarps * G) {
+            double* part = a.partials + ((int64_t)b * a.rows + q) * L * 4;
+            if (q < a.n2)
+                sweep_chunk<TabT, S_T, DIR, 2, DTAUS, false>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
+                                                             fscale, 0, NS, nullptr);
+            else
+                sweep_chunk<TabT, S_T, DIR, 1, DTAUS, false>(a, b, (int64_t)a.n2 * 64 + (int64_t)(q - a.n2) * 32, part,
+                                                             sm_rec, sm_rows, tab, sscale, fscale, 0, NS, nullptr);
+        }
+        return;
+    }
+    // Relay plan (all chunks 64 wide, more chunks than resident warps): the rows * (L - 1) layer-steps,
+    // chunk after chunk, are cut into runs of relay_quota steps; warp m = 4 c + w owns run m and works
+    // through it BACKWARDS: first the leading steps of the chunk that the end of its run cuts (nothing to
+    // wait for), then whole chunks, last the trailing steps of the chunk that the start of its run cuts —
+    // handed over by warp m - 1, which ran the leading steps of that chunk first of all.  Every warp is
+    // busy for the same number of steps, so the launch has no partly filled last round; every (chunk,
+    // layer) is computed by the same instructions as in a whole chunk, so the results are bit-identical.
+    const int W = a.rows * NS;                   // < 2^30 (checked by the launcher)
+    const int m = blockIdx.x * kWarps + warp;
+    const int p0 = min(m, W / a.relay_quota + 1) * a.relay_quota;      // my run: steps [p0, p) of the step line
+    for (int p = min(p0 + a.relay_quota, W); p > p0;) {
+        const int q = (p - 1) / NS, base = q * NS;
+        const int lo = max(p0, base) - base, hi = p - base;
+        p = base + lo;
+        double* part = a.partials + (int64_t)q * L * 4;
+        if (lo == 0 && hi == NS)
+            sweep_chunk<TabT, S_T, DIR, 2, DTAUS, false>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
+                                                         fscale, 0, NS, nullptr);
         else
-            sweep_chunk<TabT, S_T, DIR, 1, DTAUS>(a, b, (int64_t)a.n2 * 64 + (int64_t)(q - a.n2) * 32, part,
-                                                  sm_rec, sm_rows, tab, sscale, fscale);
+            sweep_chunk<TabT, S_T, DIR, 2, DTAUS, true>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
+                                                        fscale, lo, hi, a.relay_flags + q);
     }
 }
 
@@ -1269,15 +1345,31 @@ static int num_sms() {
 // 3 = half of the 64-wide chunks replaced by 32-wide ones (exercises the mixed kernel at test sizes)
 static int g_force_V = 0;
 
-struct SweepPlan { int n2, n1; };
-// slots = warps of one resident wave (0 = not capped: batches)
-static SweepPlan sweep_plan(int64_t n_lam, int B, int64_t slots) {
+struct SweepPlan { int n2, n1, relay_quota, relay_warps; };
+// slots = warps of one resident wave (0 = not capped: batches), NS = layer-steps of a chunk
+static SweepPlan sweep_plan(int64_t n_lam, int B, int64_t slots, int NS, bool may_relay) {
     SweepPlan p;
+    p.relay_quota = 0; p.relay_warps = 0;
     const int64_t c1 = (n_lam + 31) / 32, c2 = (n_lam + 63) / 64;
+#if SWEEP_RELAY
+    // Relay plan: more 64-wide chunks than resident warps -> equal runs of layer-steps per warp
+    // (sweep_kernel).  quota >= NS keeps every chunk in at most two pieces and gives the receiver of
+    // a piece quota - NS steps of slack.  Test hook 4 builds one at any size: 2 warps per 3 chunks.
+    if (may_relay && n_lam % 2 == 0 && B == 1 && c2 * NS < (int64_t)1 << 30 && (g_force_V == 0 || g_force_V == 4)) {
+        int64_t warps = (g_force_V == 4) ? (2 * c2 + 2) / 3 : slots;
+        if (warps > 0 && c2 > warps && (g_force_V == 4 || c2 >= SWEEP_V1_CHUNKS_PER_SM * (int64_t)num_sms())) {
+            const int64_t quota = (c2 * NS + warps - 1) / warps;
+            p.n2 = (int)c2; p.n1 = 0;
+            p.relay_quota = (int)quota;
+            p.relay_warps = (int)((c2 * NS + quota - 1) / quota);
+            return p;
+        }
+    }
+#endif
     if (n_lam % 2 != 0 || g_force_V == 1) { p.n2 = 0; p.n1 = (int)c1; return p; }
     if (g_force_V == 3) { p.n2 = (int)(c2 / 2); p.n1 = (int)((n_lam - 64 * (int64_t)p.n2 + 31) / 32); return p; }
     p.n2 = (int)c2; p.n1 = 0;
-    if (g_force_V == 2) return p;
+    if (g_force_V == 2 || g_force_V == 4) return p;
     // so small that 64-wide chunks would leave SMs without a warp (C1's 5k bins = 79 chunks on 148
     // SMs): a chunk is a serial recurrence, so halving it is the only parallelism left
     if ((int64_t)B * c2 < SWEEP_V1_CHUNKS_PER_SM * (int64_t)num_sms()) { p.n2 = 0; p.n1 = (int)c1; return p; }
@@ -1295,34 +1387,64 @@ static SweepPlan sweep_plan(int64_t n_lam, int B, int64_t slots) {
 #define SWEEP_PERSISTENT 1        // experiment knob: 0 = one CTA per kWarps chunks for every launch
 #endif
 
-template <typename TabT, int S_T, int DIR, bool DTAUS>
-static int launch_sweep_one(SweepArgs a, size_t smem, cudaStream_t st) {
-    // per device: CTAs per SM of this instantiation at the largest shared-memory size seen
-    static int resident[kMaxDevices];
-    static size_t smem_set[kMaxDevices];
-    static bool init = false;
-    if (!init) { for (int d = 0; d < kMaxDevices; ++d) { resident[d] = -1; smem_set[d] = 0; } init = true; }
+// per device and kernel: CTAs per SM at the largest shared-memory size seen
+struct SweepOcc {
+    int resident[kMaxDevices];
+    size_t smem_set[kMaxDevices];
+    bool init = false;
+};
+template <typename K>
+static int sweep_occupancy(K kern, SweepOcc& o, size_t smem, int* per_sm) {
+    if (!o.init) { for (int d = 0; d < kMaxDevices; ++d) { o.resident[d] = -1; o.smem_set[d] = 0; } o.init = true; }
     int dev = 0;
     CUDA_TRY(cudaGetDevice(&dev));
     if (dev < 0 || dev >= kMaxDevices) return set_err(FREI_E_UNSUPPORTED, "device ordinal out of range%s%s");
-    auto kern = sweep_kernel<TabT, S_T, DIR, DTAUS>;
-    if (resident[dev] < 0 || smem > smem_set[dev]) {
+    if (o.resident[dev] < 0 || smem > o.smem_set[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                                       (int)cudaSharedmemCarveoutMaxShared));
         int nb = 0;
         CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kThreads, smem));
-        resident[dev] = nb > 0 ? nb : 1;
-        smem_set[dev] = smem;
+        o.resident[dev] = nb > 0 ? nb : 1;
+        o.smem_set[dev] = smem;
     }
+    *per_sm = o.resident[dev];
+    return FREI_OK;
+}
+
+template <typename TabT, int S_T, int DIR, bool DTAUS>
+static int launch_sweep_one(SweepArgs a, size_t smem, cudaStream_t st) {
+    static SweepOcc occ, occ_relay;
+    auto kern = sweep_kernel<TabT, S_T, DIR, DTAUS, false>;
+    int per_sm = 1;
+    int rc = sweep_occupancy(kern, occ, smem, &per_sm);
+    if (rc) return rc;
     // One resident wave for a single atmosphere, with as many CTAs per SM as fit: launching fewer
     // to trade a nearly empty last round for fuller ones was measured (2, 3, 4 CTAs/SM at 100k ...
     // 600k wavelengths, scripts/ctas_scan.sh) and never won — 4 CTAs/SM are 0 ... 18 % faster than 3.
     const bool persistent = SWEEP_PERSISTENT && a.B == 1;
-    const int64_t cap = (int64_t)resident[dev] * num_sms();
-    const SweepPlan p = sweep_plan(a.n_lam, a.B, persistent ? cap * kWarps : 0);
+    int64_t cap = (int64_t)per_sm * num_sms();
+    // the relay kernel exists for sweeps without the dtaus output (every sweep of a solve but the last)
+    const bool may_relay = SWEEP_RELAY && !DTAUS && persistent && a.relay_flags;
+    SweepPlan p = sweep_plan(a.n_lam, a.B, persistent ? cap * kWarps : 0, a.L - 1, may_relay);
+    if (!DTAUS && p.relay_quota > 0) {
+        auto kern_r = sweep_kernel<TabT, S_T, DIR, false, true>;
+        int per_sm_r = 1;
+        rc = sweep_occupancy(kern_r, occ_relay, smem, &per_sm_r);
+        if (rc) return rc;
+        if (per_sm_r == per_sm || g_force_V == 4) {     // same residency as the plan assumed: every warp of the grid is resident
+            a.n2 = p.n2;
+            a.rows = p.n2;
+            a.relay_quota = p.relay_quota;
+            const unsigned blocks = (unsigned)((p.relay_warps + kWarps - 1) / kWarps);   // <= cap
+            CUDA_TRY(launch_pdl(kern_r, dim3(blocks, 1), dim3(kThreads), smem, st, a));
+            return FREI_OK;
+        }
+        p = sweep_plan(a.n_lam, a.B, cap * kWarps, a.L - 1, false);
+    }
     a.n2 = p.n2;
     a.rows = p.n2 + p.n1;
+    a.relay_quota = 0;
     unsigned blocks = (unsigned)((a.rows + kWarps - 1) / kWarps);
     if (persistent && blocks > cap) blocks = (unsigned)cap;
     CUDA_TRY(launch_pdl(kern, dim3(blocks, a.B), dim3(kThreads), smem, st, a));
@@ -1364,7 +1486,8 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
     ARG_TRY(B > 0 && L >= 3 && S > 0 && S <= kMaxS && n_lam > 0);
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
     if (partials)       // per-warp rows + chunk sums + per-atmosphere tickets
-        *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4) + 16;
+        *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4) + 16 +
+                    round16(sweep_rows_max(n_lam) * 4);
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -1396,7 +1519,7 @@ int frei_b200_spectral_setup(const double* d_lam_um, int64_t n_global, int64_t o
 }
 
 int frei_b200_debug_plan(int32_t force_V) {
-    ARG_TRY(force_V >= 0 && force_V <= 3);
+    ARG_TRY(force_V >= 0 && force_V <= 4);
     g_force_V = force_V;
     return FREI_OK;
 }
@@ -1477,8 +1600,10 @@ int frei_b200_sweep(const frei_table* tab, const frei_spectral* spec, const frei
     a.n_lam = tab->n_lam; a.B = atm->B; a.L = atm->L; a.S = tab->S; a.N_T = tab->N_T;
     a.rows = 0; a.n2 = 0;                          // set by the launcher from its plan
     a.plan_hdr = ws_plan_hdr(ws, atm->B, atm->L, tab->n_lam);
+    a.relay_quota = 0;
+    a.relay_flags = ws_relay_flags(ws, atm->B, atm->L, tab->n_lam);
     if (flux->dtype == FREI_F32) {               // fp32 arithmetic: sweep_f32.cu, same partials layout
-        const SweepPlan p = sweep_plan(tab->n_lam, atm->B, 0);
+        const SweepPlan p = sweep_plan(tab->n_lam, atm->B, 0, atm->L - 1, false);
         return frei_launch_sweep_f32(a, tab->dtype, direction, p.n2 > 0 ? 2 : 1, (cudaStream_t)stream);
     }
 #ifndef SWEEP_SMEM_PAD

@@ -158,7 +158,11 @@ int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stre
  * complete rounds of resident warps take 64-wide chunks and a last round that is at most half full
  * is cut into 32-wide ones; 32-wide only for odd wavelength counts and for problems too small to
  * give every SM two warps.  1 / 2 force 32-wide / 64-wide chunks only, 3 forces a mixed plan (half
- * of the 64-wide chunks, the rest 32-wide); 2 and 3 only take effect for even counts.
+ * of the 64-wide chunks, the rest 32-wide), 4 forces the relay plan (what the automatic plan runs
+ * for a single atmosphere with more 64-wide chunks than resident warps: the layer-steps of all chunks
+ * are dealt out in equal runs per warp and a chunk cut by a run boundary is handed from one warp to
+ * the next; forced: two warps per three chunks); 2, 3 and 4 only take effect for even counts, 4 only
+ * for a single atmosphere.
  * Process-wide; not meant for production use: it exists so that small parity cases can exercise
  * every chunk shape of the production-size kernels. */
 int frei_b200_debug_plan(int32_t force_V);

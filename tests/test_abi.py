@@ -64,7 +64,7 @@ def test_diagnostics_and_plan_hooks_validate_arguments():
     assert lib.frei_b200_diagnostics(None, None, None, None, None, None, 30, 500, None, None, None, None,
                                      None) == -1
     assert b'frei_b200_diagnostics' in lib.frei_b200_last_error()
-    assert lib.frei_b200_debug_plan(4) == -1
+    assert lib.frei_b200_debug_plan(5) == -1
     assert lib.frei_b200_debug_plan(3) == 0 and lib.frei_b200_debug_plan(0) == 0
 
 

@@ -82,7 +82,7 @@ def _has_sentinel(t):
     return bool((t.contiguous().view(torch.int64) == want).any())
 
 
-@pytest.mark.parametrize('plan', [0, 1, 2, 3])
+@pytest.mark.parametrize('plan', [0, 1, 2, 3, 4])
 @pytest.mark.parametrize('L,n_lam,S,B', [(12, 1000, 3, 1), (20, 514, 8, 1), (9, 333, 1, 1), (7, 260, 5, 1),
                                          (10, 600, 3, 3), (50, 8192, 3, 1)])
 def test_guard_bands_and_no_uninitialised_reads(plan, L, n_lam, S, B):
@@ -124,7 +124,7 @@ def test_guard_bands_fp32_sweep(n_lam):
     assert torch.isfinite(eng.dtaus.double()).all()
 
 
-@pytest.mark.parametrize('plan', [0, 2, 3])
+@pytest.mark.parametrize('plan', [0, 2, 3, 4])
 def test_repeated_runs_are_bit_identical(plan):
     """20 repetitions of two RE iterations from the same state, production-size grid (all SMs busy,
     several rounds of chunks, the reduction's ticket decided by a different CTA every time)."""
@@ -150,6 +150,41 @@ def test_repeated_runs_are_bit_identical(plan):
                 for a, b in zip(first, state):
                     assert torch.equal(a, b), f'repetition {rep} differs'
         assert _bands_intact(arena, spans)
+    finally:
+        _cabi.check(lib.frei_b200_debug_plan(0))
+
+
+@pytest.mark.parametrize('L,n_lam,S', [(30, 160_000, 3), (50, 200_000, 3), (12, 1000, 3), (100, 40_000, 8), (9, 4098, 1)])
+def test_relay_plan_is_bit_identical_to_whole_chunks(L, n_lam, S):
+    """The relay plan (automatic at 160k and 200k bins: 1.06 and 1.32 chunks per resident warp; forced
+    at the small sizes) cuts chunks between warps but computes every (chunk, layer) with the same
+    instructions as the plan of whole 64-wide chunks: fluxes, dtaus, integrals and T must not differ
+    in a single bit, sweep after sweep."""
+    import torch
+    from frei_b200 import synthetic, _cabi
+    from frei_b200.engine import FREI_EMIT, FREI_ABSORB
+    lib = _cabi.load()
+    w = synthetic.make_workload(L, n_lam, S)
+    states = {}
+    try:
+        for plan in (2, 4 if n_lam < 100_000 else 0):
+            _cabi.check(lib.frei_b200_debug_plan(plan))
+            eng, arena, spans = _guarded_engine(w)
+            snap = []
+            for _ in range(2):
+                eng.sweep(FREI_EMIT)
+                snap += [eng.F_up.clone(), eng.F_down.clone(), eng.sums.clone(), eng.T.clone()]
+                eng.sweep(FREI_ABSORB)
+                snap += [eng.F_up.clone(), eng.F_down.clone(), eng.sums.clone(), eng.T.clone()]
+            eng.sweep(FREI_EMIT, alpha_override=1.0, with_dtaus=True)
+            torch.cuda.synchronize()
+            snap += [eng.F_up.clone(), eng.F_down.clone(), eng.dtaus.clone(), eng.T.clone()]
+            assert _bands_intact(arena, spans)
+            states[plan] = snap
+            del eng, arena
+        (pa, a), (pb, b) = states.items()
+        for k, (x, y) in enumerate(zip(a, b)):
+            assert torch.equal(x, y), f'plan {pa} vs {pb}: snapshot {k} differs'
     finally:
         _cabi.check(lib.frei_b200_debug_plan(0))
 

@@ -28,7 +28,7 @@ LD = np.longdouble
 TINY = 1e-250        # fluxes below this are denormal-range attenuated starlight
 
 
-@pytest.fixture(params=['auto', 'v2', 'mixed'])
+@pytest.fixture(params=['auto', 'v2', 'mixed', 'relay'])
 def plan(request):
     """Sweep plan: automatic (32-wide warp-chunks, one wavelength per thread, for these small
     cases), forced 64-wide chunks (two per thread: the complete rounds of every production-size
@@ -36,7 +36,7 @@ def plan(request):
     ones: what a production-size launch with a short last round runs)."""
     from frei_b200 import _cabi
     lib = _cabi.load()
-    _cabi.check(lib.frei_b200_debug_plan({'auto': 0, 'v2': 2, 'mixed': 3}[request.param]))
+    _cabi.check(lib.frei_b200_debug_plan({'auto': 0, 'v2': 2, 'mixed': 3, 'relay': 4}[request.param]))
     yield request.param
     _cabi.check(lib.frei_b200_debug_plan(0))
 
@@ -906,8 +906,8 @@ def test_split_reduce_update_sequence_equals_fused_post(plan):
                 np.testing.assert_allclose(b, a, rtol=1e-12, atol=1e-300, err_msg=f'{name}, iteration {it}')
 
 
-@pytest.mark.parametrize('L,n_lam,S,force', [(100, 2050, 8, 2), (100, 2050, 8, 3), (200, 3002, 3, 2),
-                                             (200, 3002, 3, 3)])
+@pytest.mark.parametrize('L,n_lam,S,force', [(100, 2050, 8, 2), (100, 2050, 8, 3), (100, 2050, 8, 4),
+                                             (200, 3002, 3, 2), (200, 3002, 3, 3), (200, 3002, 3, 4)])
 def test_large_shapes_match_oracle(L, n_lam, S, force):
     """
     The layer counts and species counts of BASELINE configs C3 (100 layers, 8 species) and C5
