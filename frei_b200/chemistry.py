@@ -109,10 +109,7 @@ def chemistry(temperatures, pressures, species, return_vmr=False, m_bar=2.4 * U.
     P = np.atleast_1d(U.value(pressures, 'bar'))
     m_bar_g = float(U.value(m_bar, 'g'))
     species = list(species)
-    try:
-        import pyfastchem
-    except ImportError:
-        pyfastchem = None
+    pyfastchem = U.optional_module('pyfastchem')
 
     vmrs = {}
     if pyfastchem is None:

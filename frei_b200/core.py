@@ -105,11 +105,10 @@ class Spectrum(object):
 
 
 def _make_spectrum(flux, lam):
-    try:                                                    # pragma: no cover
-        from specutils import Spectrum1D
-        return Spectrum1D(flux=flux, spectral_axis=lam)
-    except ImportError:
-        return Spectrum(flux, lam)
+    specutils = U.optional_module('specutils')
+    if specutils is not None:                               # pragma: no cover
+        return specutils.Spectrum1D(flux=flux, spectral_axis=lam)
+    return Spectrum(flux, lam)
 
 
 def converged_layers(temp_hists, dT, n_zero_crossings, convergence_dT):
@@ -123,6 +122,15 @@ def converged_layers(temp_hists, dT, n_zero_crossings, convergence_dT):
     diffs = np.diff(temp_hist.T, axis=0)
     flips = np.count_nonzero(np.sign(diffs[1:]) != np.sign(diffs[:-1]), axis=0)
     return (flips > n_zero_crossings) | (np.abs(dT) < convergence_dT), temp_hist
+
+
+TRACE = None      # set to a list to collect (label, time.perf_counter()) marks of emission_spectrum (scripts/e2e_phases.py)
+
+
+def _mark(label):
+    if TRACE is not None:
+        import time
+        TRACE.append((label, time.perf_counter()))
 
 
 class _PinnedOutputs:
@@ -266,16 +274,15 @@ class Grid(object):
             raise ValueError("gather must be 'all' or 'local'")
         conv_dT = float(U.value(convergence_dT, 'K'))
         if dynamic_chemistry is None:
-            try:
-                import pyfastchem  # noqa: F401
-                dynamic_chemistry = True
-            except ImportError:
-                dynamic_chemistry = False
+            dynamic_chemistry = U.optional_module('pyfastchem') is not None
+        _mark('enter')
         eng = self._solver_engine(group)
+        _mark('engine reset')
         P = U.value(self.pressures, 'bar')
         m_bar_g = float(U.value(self.planet.m_bar, 'g'))
         L = eng.L
         temp_hists = []
+        tracked = None
         self.n_iterations = 0
         if not dynamic_chemistry and n_timesteps > 0:
             # Static mixing ratios: the convergence rule of frei/core.py:301-318 runs on the device
@@ -292,16 +299,21 @@ class Grid(object):
             eng.enable_batch_convergence(n_zero_crossings, conv_dT)
             hist = eng.history_buffer(n_timesteps)             # [n_timesteps][2][B][L], reused across solves
             flags = eng.flag_ring(max_ahead // check_every + 2)
+            main = torch.cuda.current_stream(eng.device)
+            side = eng.side_stream()                           # flag copies stay off the sweeps' stream
             pending, it, stopped = collections.deque(), 0, False
             while it < n_timesteps and not stopped:
                 eng.sweep(FREI_EMIT, T_hist=hist[it, 0])
                 eng.sweep(FREI_ABSORB, T_hist=hist[it, 1])
                 it += 1
-                if it % check_every == 0:
+                if it % check_every == 0 and it < n_timesteps:
                     slot = (it // check_every) % flags.shape[0]
-                    flags[slot].copy_(eng.active[:1], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record()
+                    side.wait_stream(main)
+                    with torch.cuda.stream(side):
+                        eng.active.record_stream(side)
+                        flags[slot].copy_(eng.active[:1], non_blocking=True)
+                        ev = torch.cuda.Event()
+                        ev.record()
                     pending.append((ev, slot, it))
                 if pending and it - pending[0][2] >= max_ahead:
                     pending[0][0].synchronize()
@@ -309,12 +321,12 @@ class Grid(object):
                     _, slot, _ = pending.popleft()
                     if int(flags[slot, 0]) == 0:
                         stopped = True
-            still = bool(eng.active.any().item())              # synchronises
-            eng.check_errors()
-            self.n_iterations = it if still else int(eng.iterations_done[0].item())
+            _mark('iterations queued')
+            # No synchronisation here: a converged atmosphere ignores the sweeps queued behind its
+            # last one, so the final emit and the copies of the results follow at once and the host
+            # waits a single time, for everything (below).
+            tracked = (it, eng.active, eng.iterations_done, hist)
             eng.disable_batch_convergence()
-            h = hist[:self.n_iterations, :, 0, :].cpu().numpy()                       # [n][2][L]
-            temp_hists = [h[k].T for k in range(self.n_iterations)]
         for it in range(n_timesteps if dynamic_chemistry else 0):
             if it > 0:
                 eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
@@ -328,13 +340,11 @@ class Grid(object):
             conv, _ = converged_layers(temp_hists, dT, n_zero_crossings, conv_dT)
             if np.all(conv):
                 break
-        temp_hist = np.hstack(temp_hists) if temp_hists else np.zeros((L, 0))
-        if temp_hists:
-            temp_hist = temp_hist.T[temp_hist[0] != 0].T
         if dynamic_chemistry and n_timesteps > 0:
             eng.set_mmr(self._mmr(eng.get_T()[0], P, m_bar_g))
         # final emit: alpha is not forwarded -> default 1 (frei/core.py:323-333)
         eng.sweep(FREI_EMIT, alpha_override=1.0, with_dtaus=True)
+        _mark('final emit queued')
         spec_local = eng.F_up[0, L - 1]
         dtaus_local = eng.dtaus[0]
         lam_out = self.lam
@@ -355,13 +365,33 @@ class Grid(object):
         else:
             out[0].copy_(spec_local, non_blocking=True)
             out[1:].copy_(dtaus_local, non_blocking=True)
-        final_temps = eng.T[0].cpu().numpy()                   # synchronises the stream
+        small = eng.pinned_results(n_timesteps)                # T, history, flag, iteration count
+        small['T'].copy_(eng.T[0], non_blocking=True)
+        if tracked is not None:
+            n_q, active_dev, iters_dev, hist = tracked
+            if n_q:
+                small['hist'][:n_q].copy_(hist[:n_q, :, 0, :], non_blocking=True)
+            small['active'].copy_(active_dev[:1], non_blocking=True)
+            small['iters'].copy_(iters_dev[:1], non_blocking=True)
+        _mark('copies queued')
+        torch.cuda.current_stream(eng.device).synchronize()    # the one wait of a solve
+        _mark('results on host')
         eng.check_errors()
+        final_temps = small['T'].numpy().copy()
+        if tracked is not None:
+            self.n_iterations = n_q if int(small['active'][0]) else int(small['iters'][0])
+            h = small['hist'][:self.n_iterations].numpy()                             # [n][2][L]
+            temp_hists = [h[k].T.copy() for k in range(self.n_iterations)]
+        temp_hist = np.hstack(temp_hists) if temp_hists else np.zeros((L, 0))
+        if temp_hists:
+            temp_hist = temp_hist.T[temp_hist[0] != 0].T
         arr = self._outputs.hand_out(out)
         spec, dtaus = arr[0], arr[1:]
         self.engine = eng
-        return (_make_spectrum(U.wrap(spec, 'flux'), lam_out), U.wrap(final_temps, 'K'),
-                U.wrap(temp_hist, 'K'), dtaus)
+        res = (_make_spectrum(U.wrap(spec, 'flux'), lam_out), U.wrap(final_temps, 'K'),
+               U.wrap(temp_hist, 'K'), dtaus)
+        _mark('return')
+        return res
 
     def _solver_engine(self, group):
         """Device state of this Grid, built once and reset for every solve."""

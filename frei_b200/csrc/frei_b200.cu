@@ -956,7 +956,10 @@ sweep_kernel(SweepArgs a) {
     pdl_wait();                                  // records, T, active flags come from the previous kernel
     if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: post_kernel may queue up behind it
     if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by post_kernel
-    if (a.active && !a.active[b]) return;        // converged atmosphere of a batch: nothing to do
+    // converged atmosphere of a batch: nothing to do.  A single tracked atmosphere (Grid.emission_spectrum)
+    // consumes the flag only after the records have arrived, so that its load overlaps theirs
+    const unsigned act = a.active ? a.active[b] : 1u;
+    if (gridDim.y > 1 && !act) return;
     const int L = a.L, rec8 = a.lp.rec8;
     if (tid < 32) tab[tid] = kExp2Tab[tid];
     const double sscale = a.sigma_scale ? a.sigma_scale[b] : 1.0;
@@ -986,6 +989,7 @@ sweep_kernel(SweepArgs a) {
                          : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
         }
     }
+    if (!act) return;
 
     const int G = gridDim.x, NS = L - 1;
     if (!RELAY) {
@@ -1095,6 +1099,17 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
                                                 const LevelView& lv, double* sm_T) {
     const int i = threadIdx.x, L = u.L;
     double dT = 0.0, T1 = 0.0;
+    // tracker state of this level, loaded ahead of the thermodynamics it does not depend on
+    double trk_T = 0.0;
+    int trk_sgn = 2, trk_flips = 0, trk_ncol = 0;
+    if (u.trk_T) {
+        trk_ncol = u.trk_ncol[b];
+        if (i < L) {
+            const int64_t li = (int64_t)b * L + i;
+            trk_T = u.trk_T[li];
+            trk_sgn = u.trk_state[li * 2]; trk_flips = u.trk_state[li * 2 + 1];
+        }
+    }
     if (i < L) {
         T1 = lv.T[i];
         dT = delta_T_level(u, b, i, sums_b + i * 4, lv.T, lv.P);
@@ -1115,13 +1130,13 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
         bool conv = true;
         if (i < L) {
             const int64_t li = (int64_t)b * L + i;
-            const int ncol = u.trk_ncol[b];
-            int sgn_prev = u.trk_state[li * 2], flips = u.trk_state[li * 2 + 1];
+            const int ncol = trk_ncol;
+            int sgn_prev = trk_sgn, flips = trk_flips;
             if (ncol > 0) {
                 // np.sign(diffs[1:]) != np.sign(diffs[:-1]) (core.py:308): a NaN difference compares
                 // unequal to everything, itself included, so an atmosphere whose explicit update has
                 // diverged collects a "sign change" per column and is stopped by the rule (code 3)
-                const double d = Tn - u.trk_T[li];
+                const double d = Tn - trk_T;
                 const int sgn = (d != d) ? 3 : (d > 0.0) - (d < 0.0);
                 if (sgn_prev != 2 && (sgn != sgn_prev || sgn == 3)) ++flips;
                 sgn_prev = sgn;
@@ -1133,7 +1148,7 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
         }
         const int all_conv = __syncthreads_and(conv ? 1 : 0);
         if (i == 0) {
-            const int ncol = u.trk_ncol[b] + 1;
+            const int ncol = trk_ncol + 1;
             u.trk_ncol[b] = ncol;
             if (u.direction == FREI_ABSORB && all_conv && u.active) {
                 u.active[b] = 0;
@@ -1247,8 +1262,8 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
     if (q.do_prep && q.axes_smem) stage_axes(pa.axis_P, pa.axis_T, pa.S, pa.N_P, pa.N_T, sm_axes);
     pdl_wait();                                  // partials come from the sweep before
     pdl_launch_dependents();                     // the next sweep's CTAs may line up behind the serial tail
-    if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
     const int rows = q.plan_hdr[0];
+    if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
     const int rows_per_chunk = (rows + q.nchunks - 1) / q.nchunks;
     const int r0 = min(rows, chunk * rows_per_chunk), r1 = min(rows, r0 + rows_per_chunk);
     const double* p = q.partials + ((int64_t)b * rows + r0) * n;

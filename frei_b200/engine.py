@@ -428,6 +428,26 @@ class Engine:
         ring.fill_(1)
         return ring
 
+    def side_stream(self):
+        """A second stream of this device for small copies that must not sit between two sweeps."""
+        torch = _torch()
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
+    def pinned_results(self, n_iterations):
+        """Pinned host buffers for the small results of a solve (first atmosphere): T [L], history
+        [n][2][L], the convergence flag and the iteration count (cached)."""
+        torch = _torch()
+        res = getattr(self, '_pinned_small', None)
+        if res is None or res['hist'].shape[0] < n_iterations:
+            res = dict(T=torch.empty(self.L, dtype=torch.float64).pin_memory(),
+                       hist=torch.empty((max(n_iterations, 32), 2, self.L), dtype=torch.float64).pin_memory(),
+                       active=torch.ones(1, dtype=torch.uint8).pin_memory(),
+                       iters=torch.zeros(1, dtype=torch.int32).pin_memory())
+            self._pinned_small = res
+        return res
+
     def read_history(self):
         """(T after emit, T after absorb, dT of the absorb sweep) as host arrays [B][L]; syncs."""
         torch = _torch()

@@ -21,6 +21,12 @@ for rep in range(3):
     torch.cuda.synchronize()
     print('emission_spectrum(K=%d): %.3f ms' % (K, 1e3 * (time.perf_counter() - t0)))
     del out
+from frei_b200 import core
+core.TRACE = []
+out = grid.emission_spectrum(n_timesteps=K, n_zero_crossings=10 ** 9, convergence_dT=0)
+marks, core.TRACE = core.TRACE, None
+del out
+print('marks inside emission_spectrum [ms since enter]: ' + ' | '.join('%s %.3f' % (lab, 1e3 * (t - marks[0][1])) for lab, t in marks))
 eng = grid.engine
 # phases
 torch.cuda.synchronize(); t0 = time.perf_counter()
