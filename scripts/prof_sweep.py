@@ -14,6 +14,7 @@ ap.add_argument('--config', default='C2')
 ap.add_argument('--iters', type=int, default=3)
 ap.add_argument('--table-dtype', type=int, default=64)
 ap.add_argument('--nlam', type=int, default=0)
+ap.add_argument('--flux-dtype', type=int, default=64)
 ap.add_argument('--plan', type=int, default=0)
 a = ap.parse_args()
 from frei_b200 import _cabi  # noqa: E402
@@ -26,7 +27,8 @@ w = synthetic.make_workload(L, n_lam, S, T_ref, table_f32=(dt == FREI_F32))
 tab = synthetic.device_table(w, dt)
 pl = w['planet']
 eng = Engine(tab, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'], m_bar=pl['m_bar'],
-             alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'])
+             alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'],
+             flux_dtype=FREI_F32 if a.flux_dtype == 32 else FREI_F64)
 for _ in range(a.iters):
     eng.sweep(FREI_EMIT)
     eng.sweep(FREI_ABSORB)
