@@ -122,7 +122,7 @@ typedef struct {
     void*   layer_params;  /* written by layer_prep, read by kappa / sweep */
     double* partials;      /* written by sweep, read by reduce; must be zero-filled once
                               before first use (the library leaves its ticket counters
-                              at zero after every call)                    */
+                              and the sweep's relay flags at zero after every call) */
     double* sums;          /* [B][L][4]: wavelength integrals of F2_up, F2_down, F1_up,
                               F1_down per layer-step (the four bolometric_flux calls,
                               frei/twostream.py:396-398, 524-527)          */

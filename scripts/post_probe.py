@@ -24,8 +24,14 @@ def timed(fn, n=200):
     return e0.elapsed_time(e1) / n * 1e3
 
 
-for n_lam in [int(x) for x in sys.argv[1:]] or [5_000, 200_000, 800_000]:
-    w = synthetic.make_workload(50, n_lam, 3, 2400.0)
+import argparse  # noqa: E402
+ap = argparse.ArgumentParser()
+ap.add_argument('nlam', type=int, nargs='*', default=[5_000, 200_000, 800_000])
+ap.add_argument('--L', type=int, default=50)
+ap.add_argument('--S', type=int, default=3)
+args = ap.parse_args()
+for n_lam in args.nlam:
+    w = synthetic.make_workload(args.L, n_lam, args.S, 2400.0)
     tab = synthetic.device_table(w, FREI_F64)
     pl = w['planet']
     eng = Engine(tab, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'], m_bar=pl['m_bar'],
