@@ -74,6 +74,7 @@ SIGNATURES = {
                                            c_void_p, c_void_p, c_void_p]),
     'frei_b200_debug_math': (C.c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     'frei_b200_debug_plan': (C.c_int, [c_int32]),
+    'frei_b200_debug_plan_query': (C.c_int, [c_int64, c_int32, c_int32, c_int64, c_int32, C.POINTER(c_int32)]),
     'frei_b200_layer_prep': (C.c_int, [P(frei_table), P(frei_atmosphere), P(frei_workspace),
                                        c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     'frei_b200_kappa': (C.c_int, [P(frei_table), P(frei_spectral), P(frei_atmosphere),

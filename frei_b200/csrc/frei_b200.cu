@@ -1539,6 +1539,14 @@ int frei_b200_debug_plan(int32_t force_V) {
     return FREI_OK;
 }
 
+int frei_b200_debug_plan_query(int64_t n_lam, int32_t B, int32_t L, int64_t resident_warps, int32_t may_relay,
+                               int32_t* out4) {
+    ARG_TRY(n_lam > 0 && B > 0 && L >= 3 && resident_warps >= 0 && out4);
+    const SweepPlan p = sweep_plan(n_lam, B, resident_warps, L - 1, may_relay != 0);
+    out4[0] = p.n2; out4[1] = p.n1; out4[2] = p.relay_quota; out4[3] = p.relay_warps;
+    return FREI_OK;
+}
+
 int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stream) {
     ARG_TRY(d_x && d_out && n > 0);
     debug_math_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(d_x, d_out, n);

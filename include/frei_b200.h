@@ -167,6 +167,14 @@ int frei_b200_debug_math(const double* d_x, double* d_out, int64_t n, void* stre
  * every chunk shape of the production-size kernels. */
 int frei_b200_debug_plan(int32_t force_V);
 
+/* Test hook (host only, no device needed): the plan the sweep launcher would choose for n_lam
+ * wavelengths, B atmospheres of L levels and `resident_warps` warps in one resident wave (0 = not
+ * capped: batches).  out4 = {64-wide chunks, 32-wide chunks, relay quota (layer-steps per warp, 0 = whole
+ * chunks), warps of the relay grid}.  With a relay quota q the layer-steps of the 64-wide chunks,
+ * chunk after chunk, are cut into runs of q: warp m owns steps [m q, (m + 1) q). */
+int frei_b200_debug_plan_query(int64_t n_lam, int32_t B, int32_t L, int64_t resident_warps, int32_t may_relay,
+                               int32_t* out4);
+
 /* K0.  Bracket (P_i, T_i) of every level in every species' axes with the rule
  * of scipy.interpolate's find_indices (reached from frei/opacity.py:261-263),
  * build mmr-premultiplied corner weights (zero when out of bounds:

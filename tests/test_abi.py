@@ -3,6 +3,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 from frei_b200 import _cabi
@@ -94,3 +95,82 @@ def test_product_code_never_imports_the_oracle():
             if f.endswith('.py'):
                 text = open(os.path.join(dirpath, f)).read()
                 assert not pat.search(text), f'{f} imports the oracle'
+
+
+def _relay_pieces(rows, NS, quota, n_warps):
+    """The work items of every warp of a relay launch, in execution order — a restatement of the loop
+    in sweep_kernel<..., RELAY = true>: warp m owns steps [m q, (m + 1) q) of the chunk-major step line
+    and works through them backwards."""
+    W = rows * NS
+    out = []
+    for m in range(n_warps):
+        p0 = min(m, W // quota + 1) * quota
+        p = min(p0 + quota, W)
+        items = []
+        while p > p0:
+            q = (p - 1) // NS
+            base = q * NS
+            lo, hi = max(p0, base) - base, p - base
+            p = base + lo
+            items.append((q, lo, hi))
+        out.append(items)
+    return out
+
+
+@pytest.mark.parametrize('n_lam,L,warps', [(200_000, 50, 2368), (160_000, 50, 2368), (125_000, 100, 1184),
+                                            (250_000, 200, 2368), (1_000_000, 100, 1184), (151_554, 50, 2368),
+                                            (303_106, 30, 2368)])
+def test_relay_plan_schedule_properties(n_lam, L, warps):
+    """Host logic of the relay plan (no GPU): every (chunk, layer-step) is computed exactly once, a
+    chunk is cut into at most two pieces, the first piece is the first thing its warp does and belongs
+    to the warp just below the one that finishes the chunk last of all, with quota - (L - 1) >= 0
+    steps of slack, and no warp works longer than the quota."""
+    lib = _cabi.load()
+    out = (C.c_int32 * 4)()
+    assert lib.frei_b200_debug_plan(0) == 0
+    assert lib.frei_b200_debug_plan_query(n_lam, 1, L, warps, 1, out) == 0
+    n2, n1, quota, n_warps = list(out)
+    NS = L - 1
+    rows = (n_lam + 63) // 64
+    assert rows > warps, 'test cases are meant to need a relay plan'
+    assert (n2, n1) == (rows, 0) and quota >= NS and 0 < n_warps <= warps
+    assert quota == -(-rows * NS // warps)
+    sched = _relay_pieces(rows, NS, quota, 4 * ((n_warps + 3) // 4))       # whole CTAs are launched
+    seen = np.zeros((rows, NS), dtype=np.int32)
+    pieces = {}
+    for m, items in enumerate(sched):
+        assert sum(hi - lo for _, lo, hi in items) <= quota
+        done = 0
+        for order, (q, lo, hi) in enumerate(items):
+            assert 0 <= lo < hi <= NS
+            seen[q, lo:hi] += 1
+            pieces.setdefault(q, []).append((lo, hi, m, order, done, len(items)))
+            done += hi - lo
+    assert (seen == 1).all()
+    for q, ps in pieces.items():
+        assert len(ps) <= 2
+        if len(ps) == 2:
+            (lo_a, hi_a, m_a, ord_a, start_a, _), (lo_b, hi_b, m_b, ord_b, start_b, n_b) = sorted(ps)
+            assert lo_a == 0 and hi_a == lo_b and hi_b == NS
+            assert m_b == m_a + 1                    # the receiver is the next warp: same or next CTA
+            assert ord_a == 0 and start_a == 0       # the sender runs its piece first of all
+            assert ord_b == n_b - 1                  # the receiver runs its piece last
+            if m_b < n_warps - 1:                    # slack in layer-steps between hand-over and use
+                assert start_b - hi_a == quota - NS
+            # the last warp's run may be short: it then waits for its sender, but never beyond the quota
+            assert max(start_b, hi_a) + (NS - lo_b) <= quota
+
+
+def test_plan_query_without_relay_and_small_problems():
+    lib = _cabi.load()
+    out = (C.c_int32 * 4)()
+    # more resident warps than chunks: whole 64-wide chunks
+    assert lib.frei_b200_debug_plan_query(100_000, 1, 50, 2368, 1, out) == 0
+    assert list(out) == [1563, 0, 0, 0]
+    # relay not allowed (dtaus sweep) or a batch: whole chunks as well
+    assert lib.frei_b200_debug_plan_query(200_000, 1, 50, 2368, 0, out) == 0 and list(out) == [3125, 0, 0, 0]
+    assert lib.frei_b200_debug_plan_query(200_000, 4, 50, 0, 1, out) == 0 and list(out) == [3125, 0, 0, 0]
+    # odd wavelength count and C1 (too few chunks for the SMs): 32-wide chunks
+    assert lib.frei_b200_debug_plan_query(5_001, 1, 50, 2368, 1, out) == 0 and list(out) == [0, 157, 0, 0]
+    assert lib.frei_b200_debug_plan_query(5_000, 1, 50, 2368, 1, out) == 0 and list(out) == [0, 157, 0, 0]
+    assert lib.frei_b200_debug_plan_query(0, 1, 50, 2368, 1, out) == -1
