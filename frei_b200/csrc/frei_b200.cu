@@ -106,6 +106,20 @@ static inline unsigned int* ws_relay_flags(const frei_workspace* ws, int B, int 
 }
 
 // ---------------------------------------------------------------------------
+// PROBE build only: time stamps (globaltimer, ns) of the sweep -> post -> sweep hand-over
+#ifdef POST_STAMPS
+__device__ unsigned long long g_stamps[32];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define STAMP_MAX(i) atomicMax(&g_stamps[i], gtime())
+#define STAMP_MIN(i) atomicMin(&g_stamps[i], gtime())
+extern "C" int frei_b200_debug_stamps(unsigned long long* out, int reset) {
+    if (reset) { unsigned long long z[32]; for (int i = 0; i < 32; ++i) z[i] = (i & 1) ? 0ull : ~0ull; return (int)cudaMemcpyToSymbol(g_stamps, z, sizeof(z)); }
+    return (int)cudaMemcpyFromSymbol(out, g_stamps, sizeof(g_stamps));
+}
+#else
+#define STAMP_MAX(i)
+#define STAMP_MIN(i)
+#endif
 // K0: brackets, weights, per-layer scalars
 // ---------------------------------------------------------------------------
 // scipy find_indices rule: below grid -> 0; >= last node -> n-2; else x[i] <= v < x[i+1].
@@ -159,7 +173,13 @@ __device__ __forceinline__ void stage_axes(const double* axis_P, const double* a
 // synchronised by the caller; null = search in global memory).  One thread per (level, species)
 // pair, then one per level for the scalars and the same-cell flag.  Callers that have just
 // written T synchronise first; this function ends with all records written (no trailing barrier).
-__device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const double* sm_axes, const LevelView& lv) {
+__device__ __forceinline__ double fast_rcp(double x);     // defined with the other fp64 building blocks below
+
+// `has_T` = a.has_T or a copy of it in shared memory, `g` = a.g[b] (post_kernel loads both before it
+// waits for the sweep: a load from global memory here is a full L2 round trip on the critical path).
+// `dpg_mine` (nullable): (p1 - p2)/g of level threadIdx.x, computed ahead of time by the caller.
+__device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const double* sm_axes, const LevelView& lv,
+                                           const int32_t* has_T, double g, const double* dpg_mine = nullptr) {
     const int L = a.L, S = a.S;
     const double* axP = sm_axes ? sm_axes : a.axis_P;
     const double* axT = sm_axes ? sm_axes + S * a.N_P : a.axis_T;
@@ -176,7 +196,7 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const doubl
         const double wp = (vp - xp[ip]) / (xp[ip + 1] - xp[ip]);
         bool out = (vp < xp[0]) || (vp > xp[a.N_P - 1]);
         int it = 0; double wt = 0.0;
-        if (a.has_T[s]) {
+        if (has_T[s]) {
             it = bracket_index(xt, a.N_T, vt);
             wt = (vt - xt[it]) / (xt[it + 1] - xt[it]);
             out = out || (vt < xt[0]) || (vt > xt[a.N_T - 1]);
@@ -196,8 +216,9 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const doubl
         if (a.wT) a.wT[li * S + s] = wt;
         if (a.oob) a.oob[li * S + s] = out ? 1 : 0;
     }
+    if (threadIdx.x == 0) { STAMP_MAX(31); }                         // probe: brackets of (level 0, species 0) written
     __syncthreads();                                     // offsets of the neighbouring level
-    const double g = a.g[b];
+    if (threadIdx.x == 0) { STAMP_MAX(15); }                         // probe: all brackets written
     for (int i = threadIdx.x; i < L; i += blockDim.x) {
         const int64_t li = (int64_t)b * L + i;
         double* rec = a.lp.rec + li * a.lp.rec8;
@@ -205,8 +226,9 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const doubl
         double p2;
         if (i == L - 1) p2 = p1 * (P[L - 2] * FREI_BAR) / (P[L - 3] * FREI_BAR);   // twostream.py:359
         else p2 = P[i + 1] * FREI_BAR;
-        rec[0] = (p1 - p2) / g;                                                    // twostream.py:231
-        rec[1] = 1.0 / T[i];
+        rec[0] = (dpg_mine && i == (int)threadIdx.x) ? *dpg_mine : (p1 - p2) / g;   // twostream.py:231
+        const double Ti = T[i];                          // 1/T: the kernels' reciprocal (<= 0.6 ulp) for ordinary
+        rec[1] = (Ti > 1e-3 && Ti < 1e9) ? fast_rcp(Ti) : 1.0 / Ti;   // temperatures, IEEE division otherwise
         // same (P, T) cell as level i - 1 for every species?
         int64_t same = 0;
         if (i > 0) {
@@ -233,7 +255,7 @@ __global__ void prep_kernel(PrepArgs a, int use_smem) {
         __syncthreads();
     }
     prep_block(a, blockIdx.x, use_smem ? sm_prep : nullptr,
-               global_levels(a.T, a.P, a.mmr, blockIdx.x, a.L, a.S));
+               global_levels(a.T, a.P, a.mmr, blockIdx.x, a.L, a.S), a.has_T, a.g[blockIdx.x]);
 }
 
 // ---------------------------------------------------------------------------
@@ -953,9 +975,14 @@ sweep_kernel(SweepArgs a) {
     __shared__ double tab[32];                   // 2^(j/32) for exp_neg
     const int tid = threadIdx.x, warp = tid >> 5;
     const int b = blockIdx.y;
+    constexpr int SB = (DIR == FREI_EMIT) ? 0 : 8;                   // probe: absorb sweeps stamp 8 slots higher
+    if (tid == 0) { STAMP_MIN(14 + SB); }                            // sweep CTA resident (before the wait)
     pdl_wait();                                  // records, T, active flags come from the previous kernel
+    if (tid == 0) { STAMP_MIN(16 + SB); STAMP_MAX(17 + SB); }        // sweep released
+    // the row count for post_kernel, which reads it BEFORE its griddepcontrol.wait: written and fenced
+    // before this CTA lets the dependent kernel be scheduled (it starts when every CTA has done so)
+    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) { a.plan_hdr[0] = a.rows; __threadfence(); }
     if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: post_kernel may queue up behind it
-    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by post_kernel
     // converged atmosphere of a batch: nothing to do.  A single tracked atmosphere (Grid.emission_spectrum)
     // consumes the flag only after the records have arrived, so that its load overlaps theirs
     const unsigned act = a.active ? a.active[b] : 1u;
@@ -990,6 +1017,7 @@ sweep_kernel(SweepArgs a) {
         }
     }
     if (!act) return;
+    if (tid == 0) { STAMP_MIN(18 + SB); STAMP_MAX(19 + SB); }        // records in shared memory
 
     const int G = gridDim.x, NS = L - 1;
     if (!RELAY) {
@@ -1027,6 +1055,7 @@ sweep_kernel(SweepArgs a) {
             sweep_chunk<TabT, S_T, DIR, 2, DTAUS, true>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
                                                         fscale, lo, hi, a.relay_flags + q);
     }
+    if ((tid & 31) == 0) { STAMP_MIN(20 + SB); STAMP_MAX(21 + SB); } // warp done
 }
 
 // ---------------------------------------------------------------------------
@@ -1051,42 +1080,133 @@ struct UpdateArgs {
 
 // dT of level i of atmosphere b from its four wavelength integrals s[0..3]
 // (div_bol_net_flux, convective_flux, delta_t_i, delta_temperature; twostream.py:23-43, 190-287)
-__device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int i, const double* s,
-                                                const double* Tb, const double* Pb) {
+// Pressure-only part of delta_T_level: the same in every sweep of a solve.  post_kernel computes it
+// before it waits for the sweep (thread i = level i), so that the loads of g, m_bar and alpha, one of
+// the two logarithms and half of the divisions are off the critical path between two sweeps.
+struct LevelPre {
+    double dpg;      // (p1 - p2) / g                                   twostream.py:238
+    double kz;       // k_B / (m_bar g) log(p1 / p2):  dz = kz T_1      :186-187
+    double kz_def;   // the same with the default mean mass 2.4 m_p     :403-405
+    double gcp;      // g / c_p                                         :241-266
+    double lmix_c;   // alpha k_B / (m_bar g):  mixing length = lmix_c T_1   :270
+    double dtr_c;    // c_p p1 / sigma_SB / g:  dt_rad = dtr_c / T_1^3  :37
+    double g, cp;
+    double rdpg;     // g / (p1 - p2)
+};
+__device__ __forceinline__ LevelPre level_pre(const UpdateArgs& u, int b, int i, const double* Pb) {
+    const int L = u.L;
+    LevelPre q;
+    const double g = u.g[b], m_bar = u.m_bar[b];
+    const double alpha = (u.alpha_override >= 0.0) ? u.alpha_override : u.alpha[b];
+    const double p1 = Pb[i] * FREI_BAR;
+    double p2;
+    if (i == L - 1) p2 = p1 * (Pb[L - 2] * FREI_BAR) / (Pb[L - 3] * FREI_BAR);   // :358-363
+    else p2 = Pb[i + 1] * FREI_BAR;
+    const double lg = log(p1 / p2);
+    q.g = g; q.cp = cp_of(m_bar);
+    q.dpg = (p1 - p2) / g;
+    q.kz = FREI_KB / (m_bar * g) * lg;
+    q.kz_def = FREI_KB / (2.4 * FREI_MP * g) * lg;
+    q.gcp = g / q.cp;
+    q.lmix_c = alpha * FREI_KB / (m_bar * g);
+    q.dtr_c = q.cp * p1 / FREI_SIGSB / g;
+    q.rdpg = g / (p1 - p2);
+    return q;
+}
+
+// dT of a level from its temperatures and dF_rad with the IEEE division, sqrt, log and exp of the
+// CUDA math library: the path of every input the short forms below do not cover (non-positive or
+// non-finite temperatures of an atmosphere whose explicit update is diverging, |X| outside
+// 1e-290 .. 1e290) — NaN and infinity propagate exactly as in the reference's numpy expressions.
+__device__ __noinline__ double delta_T_general(const LevelPre& q, double T1, double T2, double dF_rad) {
+    // This chain runs in one warp after the last ticket of the reduction, i.e. it is pure latency
+    // on the critical path of every sweep: x^1.5 = x sqrt(x) and |X|^0.9 = exp(0.9 log|X|) replace
+    // the two pow() calls (~250 dependent instructions each); the results differ from pow() by
+    // < 1e-14 relative, against a parity tolerance of 1e-7 on dT.
+    const double dz = q.kz * T1;                                              // :186-187
+    const double rho = q.dpg / dz;                                            // :238
+    const double dgam = (T1 - T2) / dz - q.gcp;                               // :241-266
+    const double lmix = q.lmix_c * T1;                                        // :270
+    double F_conv = 0.0;
+    if (dgam > 0.0) F_conv = rho * q.cp * (lmix * lmix) * sqrt(q.g / T1) * (dgam * sqrt(dgam));   // :285-287
+    const double div = (dF_rad + F_conv) / dz;                                // :205
+    const double X = div * dz;
+    const double f_pre = (X != 0.0) ? 1e5 * exp(-0.9 * log(fabs(X))) : 1.0;   // :32-35
+    const double dt_rad = q.dtr_c / (T1 * T1 * T1);                           // :37
+    double dt = f_pre * dt_rad;
+    if (dgam > 0.0) dt = f_pre * fmin(dt_rad, sqrt(T1 / q.g / dgam));         // :39-43
+    // delta_temperature is called without m_bar: defaults 2.4 m_p, n_dof 5 (:403-405)
+    const double rho_def = q.dpg / (q.kz_def * T1);
+    return 1.0 / rho_def / cp_of(2.4 * FREI_MP) * div * dt;                   // :216-217
+}
+
+// log(x) for normal positive finite x: x = m 2^e with m in [sqrt(1/2), sqrt 2), log m = 2 atanh(s),
+// s = (m - 1)/(m + 1), |s| < 0.172; series to s^17 (truncation 4e-15 relative), ~25 instructions inline.
+__device__ __forceinline__ double fast_log(double x) {
+    int hi = __double2hiint(x);
+    int e = (hi >> 20) - 1023;
+    double m = __hiloint2double((hi & 0x000fffff) | 0x3ff00000, __double2loint(x));      // [1, 2)
+    const bool big = m > 1.4142135623730951;
+    m = big ? 0.5 * m : m;
+    e += big ? 1 : 0;
+    const double sn = (m - 1.0) * fast_rcp(m + 1.0), s2 = sn * sn;
+    double p = fma(s2, 2.0 / 17.0, 2.0 / 15.0);
+    p = fma(p, s2, 2.0 / 13.0);
+    p = fma(p, s2, 2.0 / 11.0);
+    p = fma(p, s2, 2.0 / 9.0);
+    p = fma(p, s2, 2.0 / 7.0);
+    p = fma(p, s2, 2.0 / 5.0);
+    p = fma(p, s2, 2.0 / 3.0);
+    const double lm = fma(sn * s2, p, sn + sn);
+    const double de = (double)e;
+    return fma(de, 0.6931471803691238, fma(de, 1.9082149292705877e-10, lm));    // ln 2 in two parts
+}
+
+// dT of level i of atmosphere b from its four wavelength integrals s[0..3]
+// (div_bol_net_flux, convective_flux, delta_t_i, delta_temperature; twostream.py:23-43, 190-287).
+// This chain runs in one warp after the last ticket of the reduction — pure latency between two
+// sweeps, and cold straight-line code: with the library's division / sqrt / log / exp it took 3.8 us
+// (time stamps, scripts/stamp_probe.py), mostly instruction fetch.  The short forms use the
+// kernels' own reciprocal, square root and exponential (<= 1.5 ulp each) and a series logarithm;
+// the result differs from the library path by ~1e-15 relative, against a parity tolerance of 1e-7.
+__device__ __forceinline__ double delta_T_level(const UpdateArgs& u, const LevelPre& q, int i, const double* s,
+                                                const double* Tb) {
     const int L = u.L;
     const bool active = (u.direction == FREI_EMIT) ? (i >= 1) : (i <= L - 2);
     if (!active) return 0.0;                                  // dT[0] = 0 (emit), dT[L-1] = 0 (absorb)
     const double T1 = Tb[i];
-    const double g = u.g[b], m_bar = u.m_bar[b];
-    const double alpha = (u.alpha_override >= 0.0) ? u.alpha_override : u.alpha[b];
-    const double p1 = Pb[i] * FREI_BAR;
-    double p2, T2;
-    if (i == L - 1) { p2 = p1 * (Pb[L - 2] * FREI_BAR) / (Pb[L - 3] * FREI_BAR); T2 = T1; }   // :358-363
-    else { p2 = Pb[i + 1] * FREI_BAR; T2 = Tb[i + 1]; }
+    const double T2 = (i == L - 1) ? T1 : Tb[i + 1];                          // :358-363
     const double dF_rad = (s[0] - s[1]) - (s[2] - s[3]);                      // :199
-    const double cp = cp_of(m_bar);
-    // This chain runs in one warp after the last ticket of the reduction, i.e. it is pure latency
-    // on the critical path of every sweep: log(p1/p2) is taken once for both layer thicknesses,
-    // x^1.5 = x sqrt(x) and |X|^0.9 = exp(0.9 log|X|) replace the two pow() calls (~250
-    // dependent instructions each); the results differ from pow() by < 1e-14 relative, against a
-    // parity tolerance of 1e-7 on dT.
-    const double lg = log(p1 / p2);
-    const double dz = (FREI_KB * T1) / (m_bar * g) * lg;                      // :186-187
-    const double rho = ((p1 - p2) / g) / dz;                                  // :238
-    const double dgam = (T1 - T2) / dz - g / cp;                              // :241-266
-    const double lmix = alpha * FREI_KB * T1 / (m_bar * g);                   // :270
-    double F_conv = 0.0;
-    if (dgam > 0.0) F_conv = rho * cp * (lmix * lmix) * sqrt(g / T1) * (dgam * sqrt(dgam));   // :285-287
-    const double div = (dF_rad + F_conv) / dz;                                // :205
-    const double X = div * dz;
-    const double f_pre = (X != 0.0) ? 1e5 * exp(-0.9 * log(fabs(X))) : 1.0;   // :32-35
-    const double dt_rad = cp * p1 / FREI_SIGSB / g / (T1 * T1 * T1);          // :37
-    double dt = f_pre * dt_rad;
-    if (dgam > 0.0) dt = f_pre * fmin(dt_rad, sqrt(T1 / g / dgam));           // :39-43
+    const double dz = q.kz * T1;                                              // :186-187
+    const double rdz = fast_rcp(dz), rT1 = fast_rcp(T1);
+    const double rho = q.dpg * rdz;                                           // :238
+    const double dgam = (T1 - T2) * rdz - q.gcp;                              // :241-266
+    const double lmix = q.lmix_c * T1;                                        // :270
+    const bool conv = dgam > 0.0;
+    double rs, F_conv = 0.0, dt_conv = 0.0;
+    const double dg = conv ? dgam : 1.0;                                      // keeps the unused branch finite
+    const double sq_dg = fast_sqrt(dg, rs);
+    if (conv) {
+        double rs2;
+        F_conv = rho * q.cp * (lmix * lmix) * fast_sqrt(q.g * rT1, rs2) * (dgam * sq_dg);    // :285-287
+        dt_conv = fast_sqrt(T1 * fast_rcp(q.g), rs2) * rs;                    // sqrt(T1 / g / dgam), :41
+    }
+    const double div = (dF_rad + F_conv) * rdz;                               // :205
+    const double X = div * dz, aX = fabs(X);
+    double f_pre = 1.0;                                                       // :32-35
+    if (X != 0.0) {
+        const double w = 0.9 * fast_log(aX);                                  // |X|^-0.9 = exp(-0.9 log |X|)
+        double ew, mw;
+        exp_neg(fabs(w), kExp2Tab, ew, mw);
+        f_pre = 1e5 * (w >= 0.0 ? ew : fast_rcp(ew));
+    }
+    const double dt_rad = q.dtr_c * (rT1 * rT1 * rT1);                        // :37
+    const double dt = f_pre * (conv ? fmin(dt_rad, dt_conv) : dt_rad);        // :39-43
     // delta_temperature is called without m_bar: defaults 2.4 m_p, n_dof 5 (:403-405)
-    const double m_def = 2.4 * FREI_MP;
-    const double rho_def = ((p1 - p2) / g) / ((FREI_KB * T1) / (m_def * g) * lg);
-    return 1.0 / rho_def / cp_of(m_def) * div * dt;                           // :216-217
+    const double res = (q.kz_def * T1 * q.rdpg) * (1.0 / cp_of(2.4 * FREI_MP)) * div * dt;   // :216-217
+    const bool plain = T1 > 1e-3 && T1 < 1e9 && T2 > 1e-3 && T2 < 1e9 && (X == 0.0 || (aX > 1e-290 && aX < 1e290)) &&
+                       res == res && fabs(res) < 1e300;
+    return plain ? res : delta_T_general(q, T1, T2, dF_rad);
 }
 
 // Block-wide: thread i = level i.  All reads of T precede the barrier, all writes follow it;
@@ -1094,9 +1214,12 @@ __device__ __forceinline__ double delta_T_level(const UpdateArgs& u, int b, int 
 // and the mixing ratios of this atmosphere are read; `sm_T` (nullable) = a writable shared-memory
 // copy of T that lv.T points to: the new T is stored there as well, so K0 does not wait for a
 // global-memory round trip of what this block has just computed.
+// `pre` (nullable) = the pressure-only terms of this thread's level, `has_T` (nullable) = a shared
+// memory copy of the species' has_T flags: both prepared by the caller ahead of time.
 __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepArgs& pa, int do_prep,
                                                 int b, const double* sums_b, const double* sm_axes,
-                                                const LevelView& lv, double* sm_T) {
+                                                const LevelView& lv, double* sm_T, const LevelPre* pre,
+                                                const int32_t* has_T) {
     const int i = threadIdx.x, L = u.L;
     double dT = 0.0, T1 = 0.0;
     // tracker state of this level, loaded ahead of the thermodynamics it does not depend on
@@ -1112,9 +1235,13 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
     }
     if (i < L) {
         T1 = lv.T[i];
-        dT = delta_T_level(u, b, i, sums_b + i * 4, lv.T, lv.P);
+        const LevelPre q = pre ? *pre : level_pre(u, b, i, lv.P);
+        dT = delta_T_level(u, q, i, sums_b + i * 4, lv.T);
     }
+    if (threadIdx.x == 0) { STAMP_MAX(23); }                         // probe: dT of level 0 computed (thread 0: inactive level for emit)
+    if (threadIdx.x == 1) { STAMP_MAX(25); }                         // probe: dT of level 1 computed
     __syncthreads();
+    if (threadIdx.x == 0) { STAMP_MAX(27); }                         // probe: all levels' dT computed
     const double Tn = T1 - dT;                                                // :407, :536
     if (i < L) {
         u.dT[(int64_t)b * L + i] = dT;
@@ -1156,9 +1283,10 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
             }
         }
     }
+    if (threadIdx.x == 0) { STAMP_MAX(11); }                         // temperature update done
     if (!do_prep) return;
     __syncthreads();
-    prep_block(pa, b, sm_axes, lv);
+    prep_block(pa, b, sm_axes, lv, has_T ? has_T : pa.has_T, pre ? pre->g : pa.g[b], pre ? &pre->dpg : nullptr);
 }
 
 __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const double* __restrict__ sums,
@@ -1168,7 +1296,7 @@ __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const
     if (do_prep && use_smem) stage_axes(pa.axis_P, pa.axis_T, pa.S, pa.N_P, pa.N_T, sm_upd);   // synchronised inside
     update_and_prep(u, pa, do_prep, blockIdx.x, sums + (int64_t)blockIdx.x * u.L * 4,
                     (do_prep && use_smem) ? sm_upd : nullptr,
-                    global_levels(u.T, u.P, do_prep ? pa.mmr : nullptr, blockIdx.x, u.L, pa.S), nullptr);
+                    global_levels(u.T, u.P, do_prep ? pa.mmr : nullptr, blockIdx.x, u.L, pa.S), nullptr, nullptr, nullptr);
 }
 
 // ---------------------------------------------------------------------------
@@ -1259,23 +1387,36 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
         if (q.do_prep)
             for (int e = threadIdx.x; e < L * pa.S; e += blockDim.x) sm_mmr[e] = pa.mmr[(int64_t)b * L * pa.S + e];
     }
+    if (threadIdx.x == 0) { STAMP_MIN(0); STAMP_MAX(1); }           // post CTA entry
     if (q.do_prep && q.axes_smem) stage_axes(pa.axis_P, pa.axis_T, pa.S, pa.N_P, pa.N_T, sm_axes);
+    // also before the wait: the species' has_T flags, the pressure-only terms of the temperature
+    // update (thread i = level i; loads of g, m_bar, alpha, a logarithm and four divisions) and the
+    // number of partial rows — the sweep writes it, fenced, before it lets this kernel be scheduled
+    __shared__ int32_t sm_hasT[kMaxS];
+    if (q.do_prep && threadIdx.x < pa.S) sm_hasT[threadIdx.x] = pa.has_T[threadIdx.x];
+    LevelPre pre;
+    const bool have_pre = q.do_update && q.stage_levels;
+    if (have_pre && threadIdx.x < L) pre = level_pre(u, b, threadIdx.x, u.P + (int64_t)b * L);
+    const int rows = __ldcg(q.plan_hdr);
     pdl_wait();                                  // partials come from the sweep before
+    if (threadIdx.x == 0) { STAMP_MIN(2); STAMP_MAX(3); }           // after griddepcontrol.wait
     pdl_launch_dependents();                     // the next sweep's CTAs may line up behind the serial tail
-    const int rows = q.plan_hdr[0];
     if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
     const int rows_per_chunk = (rows + q.nchunks - 1) / q.nchunks;
     const int r0 = min(rows, chunk * rows_per_chunk), r1 = min(rows, r0 + rows_per_chunk);
     const double* p = q.partials + ((int64_t)b * rows + r0) * n;
     const double s1 = cta_column_sum(p, r1 - r0, n, sm_post, G);
     if (threadIdx.x < n) q.chunk_sums[((int64_t)b * q.nchunks + chunk) * n + threadIdx.x] = s1;
+    if (threadIdx.x == 0) { STAMP_MIN(4); STAMP_MAX(5); }           // stage 1 done
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) is_last = (atomicAdd(q.counters + b, 1u) == (unsigned)(q.nchunks - 1));
     __syncthreads();
     if (!is_last) return;
+    if (threadIdx.x == 0) { STAMP_MAX(7); }                          // last ticket taken
     __threadfence();
     double s2 = cta_column_sum(q.chunk_sums + (int64_t)b * q.nchunks * n, q.nchunks, n, sm_post, G);
+    if (threadIdx.x == 0) { STAMP_MAX(9); }                          // stage 2 done
     if (q.peer_bufs) {
         // One-shot all-reduce fused into this kernel, flag-in-data ("LL") protocol: every double of
         // this rank's [L][4] integrals is sent to every rank as two 8-byte words, each holding 32
@@ -1327,7 +1468,9 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
     if (q.stage_levels) { lv.T = sm_T; lv.P = sm_P; lv.mmr = sm_mmr; lv.off = sm_off; }
     else lv = global_levels(u.T, u.P, q.do_prep ? pa.mmr : nullptr, b, L, pa.S);
     update_and_prep(u, pa, q.do_prep, b, sm_sums, (q.do_prep && q.axes_smem) ? sm_axes : nullptr, lv,
-                    q.stage_levels ? sm_T : nullptr);
+                    q.stage_levels ? sm_T : nullptr, have_pre ? &pre : nullptr, q.do_prep ? sm_hasT : nullptr);
+    __syncthreads();
+    if (threadIdx.x == 0) { STAMP_MAX(13); }                         // records written
 }
 
 // ---------------------------------------------------------------------------
