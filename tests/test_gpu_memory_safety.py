@@ -198,3 +198,41 @@ def test_batch_tracker_and_diagnostics_guarded():
     torch.cuda.synchronize()
     assert _bands_intact(arena, spans)
     assert np.isfinite(T).all()
+
+
+@pytest.mark.parametrize('n_lam', [160_000, 20_000])
+def test_cuda_graph_replay_equals_plain_launches(n_lam):
+    """An RE iteration captured into a CUDA graph (emit, post, absorb, post) and replayed gives bit for
+    bit what the individual launches give — at 160k bins with the relay plan, whose hand-over flags
+    must be back at zero after every launch because a replay cannot change a kernel argument — and
+    a change of the engine's structs (the batch tracker) drops the captured graph instead of
+    replaying stale pointers."""
+    import torch
+    from frei_b200 import synthetic
+    from frei_b200.engine import Engine, FREI_F64
+    w = synthetic.make_workload(30, n_lam, 3)
+    tab = synthetic.device_table(w, FREI_F64)
+    pl = w['planet']
+
+    def mk():
+        return Engine(tab, w['lam_um'], w['P_bar'], w['T_init'], w['mmr'], g=pl['g'], m_bar=pl['m_bar'],
+                      alpha=pl['alpha'], T_star=pl['T_star'], a_rstar=pl['a_rstar'])
+    a, b = mk(), mk()
+    assert b.capture_iteration()
+    for _ in range(4):
+        a.iteration()
+        b.iteration()
+    torch.cuda.synchronize()
+    assert b._graph is not None
+    for name in ('T', 'F_up', 'F_down', 'sums'):
+        assert torch.equal(getattr(a, name), getattr(b, name)), name
+    assert torch.isfinite(b.T).all()
+    # structs change -> the graph is dropped, the tracker is honoured
+    b.enable_batch_convergence(n_zero_crossings=10 ** 9, convergence_dT=0.0)
+    assert b._graph is None
+    a.enable_batch_convergence(n_zero_crossings=10 ** 9, convergence_dT=0.0)
+    for _ in range(2):
+        a.iteration()
+        b.iteration()
+    torch.cuda.synchronize()
+    assert torch.equal(a.T, b.T) and torch.equal(a.F_up, b.F_up)
