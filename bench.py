@@ -490,6 +490,10 @@ def run_ours(args):
             extras['c4'] = batch_solve(args, world, rank, dev)
         except Exception as exc:                               # pragma: no cover
             extras['c4'] = {'error': repr(exc)}
+        try:
+            extras['c5'] = stress_solve(args, world, rank, dev, group)
+        except Exception as exc:                               # pragma: no cover
+            extras['c5'] = {'error': repr(exc)}
 
     if rank == 0:
         out = {
@@ -519,6 +523,40 @@ def run_ours(args):
         print(json.dumps(out))
     if world > 1:
         dist.destroy_process_group()
+
+
+def stress_solve(args, world, rank, dev, group, cap=400):
+    """BASELINE config C5: 200 layers x 2M wavelength bins in fp64, wavelength-sharded over this job's
+    GPUs, iterated to the reference's convergence rule (frei/core.py:301-318, on the device)."""
+    import torch
+    import torch.distributed as dist
+    from frei_b200.engine import FREI_F64
+    r = time_sweeps(args, 'C5', world, rank, dev, group, FREI_F64, FREI_F64, steps=2, warmup=2)
+    eng, w, L = r['eng'], r['w'], r['L']
+    eng.reset(w['T_init'])
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = eng.launches
+    ev0.record()
+    iters, T = eng.solve_batch(cap, n_zero_crossings=2, convergence_dT=3.0, check_every=4)
+    ev1.record()
+    torch.cuda.synchronize()
+    t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    n_it = int(iters[0])
+    evals = (2 * n_it + 1) * (L - 1) * r['n_lam_global']       # the final emit included
+    return {'metric': METRIC, 'value': evals / (ms * 1e-3), 'unit': UNIT, 'scaling': 'strong', 'n_gpus': world,
+            'dtype': 'f64', 'workload': 'C5: stress, 200 layers x 2M lambda bins (global), 3 species, fp64, lambda-sharded, '
+                                        'RE iteration to the convergence rule of frei/core.py:301-318 + final emit',
+            'n_layers': L, 'n_lambda_global': r['n_lam_global'],
+            'iterations': n_it, 'iteration_cap': cap, 'converged': bool(n_it < cap), 'ms_total': ms,
+            'T_finite': bool(np.isfinite(T).all()), 'T_bottom_top_K': [float(T[0, 0]), float(T[0, -1])],
+            'per_iteration_ms': r['ms'] / r['steps'], 'gpu_launches': eng.launches - l0,
+            'collective': r['collective']}
 
 
 def batch_solve(args, world, rank, dev):
