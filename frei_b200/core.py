@@ -375,6 +375,9 @@ class Grid(object):
             small['iters'].copy_(iters_dev[:1], non_blocking=True)
         _mark('copies queued')
         torch.cuda.current_stream(eng.device).synchronize()    # the one wait of a solve
+        if tracked is not None:
+            eng.side_stream().synchronize()                    # flag polls still in flight (they only depend on
+                                                               # iterations that are long done): the ring is reused
         _mark('results on host')
         eng.check_errors()
         final_temps = small['T'].numpy().copy()
