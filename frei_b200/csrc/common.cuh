@@ -95,6 +95,18 @@ struct SweepArgs {
     unsigned int* relay_flags;  // [rows], zero between launches
 };
 
+// Partial sums of the wavelength integrals: element (atmosphere b, chunk row q, level i, integral k).
+// POST_PER_LEVEL = 1: [B][L][rows][4] — the rows of a level are contiguous, because the kernel that
+// follows a sweep gives every level its own CTA; 0: [B][rows][L][4] (round 1 layout, one CTA per
+// block of rows).  `rows` = the row count of the launch (SweepArgs::rows).
+#ifndef POST_PER_LEVEL
+#define POST_PER_LEVEL 1
+#endif
+__device__ __forceinline__ double* part_base(double* partials, int b, int rows, int L, int q) {
+    return POST_PER_LEVEL ? partials + ((int64_t)b * L * rows + q) * 4 : partials + ((int64_t)b * rows + q) * L * 4;
+}
+__device__ __forceinline__ int64_t part_level_stride(int rows) { return POST_PER_LEVEL ? (int64_t)rows * 4 : 4; }
+
 // Sum four per-lane values across the warp; on return lanes 0, 8, 16, 24 hold the
 // totals of v0, v1, v2, v3 respectively.  Fixed butterfly -> deterministic.
 __device__ __forceinline__ double warp_reduce4(double v0, double v1, double v2, double v3, int lane) {

@@ -91,6 +91,7 @@ static inline LayerParams layer_params_view(void* p, int S) {
 static inline int64_t round16(int64_t x) { return (x + 15) & ~int64_t(15); }
 static inline int64_t sweep_rows_max(int64_t n_lam) { return (n_lam + 31) / 32 + 2 * kWarps; }   // bound on the plan's rows
 // ws->partials: [B][rows_max][L][4] chunk rows | [B][kPostChunks][L][4] stage-1 sums | [B] tickets | header | [rows_max] relay flags
+//               | [B][L] new temperatures | [B] converged-level counts
 static inline double* ws_chunk_sums(const frei_workspace* ws, int B, int L, int64_t n_lam) {
     return ws->partials + (int64_t)B * sweep_rows_max(n_lam) * L * 4;
 }
@@ -103,6 +104,15 @@ static inline int32_t* ws_plan_hdr(const frei_workspace* ws, int B, int L, int64
 // relay flags, one per chunk row of a single atmosphere (zero between launches)
 static inline unsigned int* ws_relay_flags(const frei_workspace* ws, int B, int L, int64_t n_lam) {
     return reinterpret_cast<unsigned int*>(ws_plan_hdr(ws, B, L, n_lam) + 4);
+}
+// per-level reduction (post_level_kernel): the new temperatures until the last CTA of an atmosphere
+// publishes them, and the count of converged levels
+static inline double* ws_T_next(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return reinterpret_cast<double*>(reinterpret_cast<char*>(ws_relay_flags(ws, B, L, n_lam)) +
+                                     round16(sweep_rows_max(n_lam) * 4));
+}
+static inline unsigned int* ws_conv_count(const frei_workspace* ws, int B, int L, int64_t n_lam) {
+    return reinterpret_cast<unsigned int*>(ws_T_next(ws, B, L, n_lam) + (int64_t)B * L);
 }
 
 // ---------------------------------------------------------------------------
@@ -175,6 +185,40 @@ __device__ __forceinline__ void stage_axes(const double* axis_P, const double* a
 // written T synchronise first; this function ends with all records written (no trailing barrier).
 __device__ __forceinline__ double fast_rcp(double x);     // defined with the other fp64 building blocks below
 
+// K0 for one (level, species) pair: bracket of (vp, vt) in the species' axes, the four mmr-premultiplied
+// corner weights and the row offset, written into the level's record; returns the offset.
+__device__ __forceinline__ int64_t prep_pair(const PrepArgs& a, int b, int i, int s, const double* axP,
+                                             const double* axT, const int32_t* has_T, double vp, double vt,
+                                             double m) {
+    const int S = a.S;
+    const int64_t li = (int64_t)b * a.L + i;
+    double* rec = a.lp.rec + li * a.lp.rec8;
+    const double* xp = axP + (int64_t)s * a.N_P;
+    const double* xt = axT + (int64_t)s * a.N_T;
+    const int ip = bracket_index(xp, a.N_P, vp);
+    const double wp = (vp - xp[ip]) / (xp[ip + 1] - xp[ip]);
+    bool out = (vp < xp[0]) || (vp > xp[a.N_P - 1]);
+    int it = 0; double wt = 0.0;
+    if (has_T[s]) {
+        it = bracket_index(xt, a.N_T, vt);
+        wt = (vt - xt[it]) / (xt[it + 1] - xt[it]);
+        out = out || (vt < xt[0]) || (vt > xt[a.N_T - 1]);
+    }
+    double w00 = (1.0 - wp) * (1.0 - wt), w01 = (1.0 - wp) * wt;
+    double w10 = wp * (1.0 - wt), w11 = wp * wt;
+    if (out) { w00 = w01 = w10 = w11 = 0.0; }       // fill_value=0, opacity.py:243
+    double* W = rec + 2 + 4 * s;
+    W[0] = m * w00; W[1] = m * w01; W[2] = m * w10; W[3] = m * w11;
+    const int64_t off = (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
+    reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s] = off;
+    if (a.iP) a.iP[li * S + s] = ip;
+    if (a.iT) a.iT[li * S + s] = it;
+    if (a.wP) a.wP[li * S + s] = wp;
+    if (a.wT) a.wT[li * S + s] = wt;
+    if (a.oob) a.oob[li * S + s] = out ? 1 : 0;
+    return off;
+}
+
 // `has_T` = a.has_T or a copy of it in shared memory, `g` = a.g[b] (post_kernel loads both before it
 // waits for the sweep: a load from global memory here is a full L2 round trip on the critical path).
 // `dpg_mine` (nullable): (p1 - p2)/g of level threadIdx.x, computed ahead of time by the caller.
@@ -187,34 +231,8 @@ __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const doubl
     const double* P = lv.P;
     for (int idx = threadIdx.x; idx < L * S; idx += blockDim.x) {
         const int i = idx / S, s = idx - i * S;
-        const int64_t li = (int64_t)b * L + i;
-        double* rec = a.lp.rec + li * a.lp.rec8;
-        const double* xp = axP + (int64_t)s * a.N_P;
-        const double* xt = axT + (int64_t)s * a.N_T;
-        const double vp = P[i], vt = T[i];
-        const int ip = bracket_index(xp, a.N_P, vp);
-        const double wp = (vp - xp[ip]) / (xp[ip + 1] - xp[ip]);
-        bool out = (vp < xp[0]) || (vp > xp[a.N_P - 1]);
-        int it = 0; double wt = 0.0;
-        if (has_T[s]) {
-            it = bracket_index(xt, a.N_T, vt);
-            wt = (vt - xt[it]) / (xt[it + 1] - xt[it]);
-            out = out || (vt < xt[0]) || (vt > xt[a.N_T - 1]);
-        }
-        const double m = lv.mmr[idx];
-        double w00 = (1.0 - wp) * (1.0 - wt), w01 = (1.0 - wp) * wt;
-        double w10 = wp * (1.0 - wt), w11 = wp * wt;
-        if (out) { w00 = w01 = w10 = w11 = 0.0; }       // fill_value=0, opacity.py:243
-        double* W = rec + 2 + 4 * s;
-        W[0] = m * w00; W[1] = m * w01; W[2] = m * w10; W[3] = m * w11;
-        const int64_t off = (int64_t)((s * a.N_P + ip) * a.N_T + it) * a.n_lam;
-        reinterpret_cast<int64_t*>(rec)[2 + 4 * S + s] = off;
+        const int64_t off = prep_pair(a, b, i, s, axP, axT, has_T, P[i], T[i], lv.mmr[idx]);
         if (lv.off) lv.off[idx] = off;
-        if (a.iP) a.iP[li * S + s] = ip;
-        if (a.iT) a.iT[li * S + s] = it;
-        if (a.wP) a.wP[li * S + s] = wp;
-        if (a.wT) a.wT[li * S + s] = wt;
-        if (a.oob) a.oob[li * S + s] = out ? 1 : 0;
     }
     if (threadIdx.x == 0) { STAMP_MAX(31); }                         // probe: brackets of (level 0, species 0) written
     __syncthreads();                                     // offsets of the neighbouring level
@@ -851,9 +869,10 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
     }
 
     double F2u[V], F1d[V], dtau[V], red[4], oth[V], nxt[V], k[V];
+    const int64_t pstride = part_level_stride(a.rows);       // from one level of this chunk's partials to the next
     auto publish = [&](const double* r, int row) {
         const double r4 = warp_reduce4(r[0], r[1], r[2], r[3], lane);
-        if ((lane & 7) == 0) part[row * 4 + (lane >> 3)] = r4;
+        if ((lane & 7) == 0) part[row * pstride + (lane >> 3)] = r4;
     };
     if (DIR == FREI_EMIT) {
         // i = 1 .. L-2 regular (other = fluxes_down[i+1], stale), i = L-1 top pseudo-layer
@@ -950,7 +969,7 @@ __device__ __forceinline__ void sweep_chunk(const SweepArgs& a, int b, int64_t j
                 gather_smem<TabT, S_T, V>(slot, rec, S, t.sg, k);
             }
         }
-        if (s0 == 0 && lane < 4) part[(L - 1) * 4 + lane] = 0.0;    // level L-1 is not visited
+        if (s0 == 0 && lane < 4) part[(L - 1) * pstride + lane] = 0.0;    // level L-1 is not visited
     }
     if (PIECES && s1 < L - 1) relay_signal(flag, lane);    // the rest of the chunk belongs to another warp
 }
@@ -1017,13 +1036,26 @@ sweep_kernel(SweepArgs a) {
         }
     }
     if (!act) return;
+#if POST_PER_LEVEL
+    // "same table rows as the level below" (bit 0 of the record's flag word): the kernel that wrote
+    // the records works one level per CTA and cannot see the neighbour's new bracket, so the flags
+    // are made here, from the row offsets of the staged records
+    for (int lev = tid; lev < L; lev += kThreads) {
+        int64_t* r1 = reinterpret_cast<int64_t*>(sm_rec + (size_t)lev * rec8);
+        int64_t same = lev > 0;
+        if (lev > 0)
+            for (int s = 0; s < a.S; ++s) if (r1[2 + 4 * a.S + s] != (r1 - rec8)[2 + 4 * a.S + s]) same = 0;
+        r1[2 + 5 * a.S] = same;
+    }
+    __syncthreads();
+#endif
     if (tid == 0) { STAMP_MIN(18 + SB); STAMP_MAX(19 + SB); }        // records in shared memory
 
     const int G = gridDim.x, NS = L - 1;
     if (!RELAY) {
         // whole chunks q = w G + c, + kWarps G, ...
         for (int q = warp * G + blockIdx.x; q < a.rows; q += kWarps * G) {
-            double* part = a.partials + ((int64_t)b * a.rows + q) * L * 4;
+            double* part = part_base(a.partials, b, a.rows, L, q);
             if (q < a.n2)
                 sweep_chunk<TabT, S_T, DIR, 2, DTAUS, false>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
                                                              fscale, 0, NS, nullptr);
@@ -1047,7 +1079,7 @@ sweep_kernel(SweepArgs a) {
         const int q = (p - 1) / NS, base = q * NS;
         const int lo = max(p0, base) - base, hi = p - base;
         p = base + lo;
-        double* part = a.partials + (int64_t)q * L * 4;
+        double* part = part_base(a.partials, 0, a.rows, L, q);
         if (lo == 0 && hi == NS)
             sweep_chunk<TabT, S_T, DIR, 2, DTAUS, false>(a, b, (int64_t)q * 64, part, sm_rec, sm_rows, tab, sscale,
                                                          fscale, 0, NS, nullptr);
@@ -1169,13 +1201,12 @@ __device__ __forceinline__ double fast_log(double x) {
 // (time stamps, scripts/stamp_probe.py), mostly instruction fetch.  The short forms use the
 // kernels' own reciprocal, square root and exponential (<= 1.5 ulp each) and a series logarithm;
 // the result differs from the library path by ~1e-15 relative, against a parity tolerance of 1e-7.
+// T1 = T of the level, T2 = T of the level above (T1 itself for the top level, :358-363)
 __device__ __forceinline__ double delta_T_level(const UpdateArgs& u, const LevelPre& q, int i, const double* s,
-                                                const double* Tb) {
+                                                double T1, double T2) {
     const int L = u.L;
     const bool active = (u.direction == FREI_EMIT) ? (i >= 1) : (i <= L - 2);
     if (!active) return 0.0;                                  // dT[0] = 0 (emit), dT[L-1] = 0 (absorb)
-    const double T1 = Tb[i];
-    const double T2 = (i == L - 1) ? T1 : Tb[i + 1];                          // :358-363
     const double dF_rad = (s[0] - s[1]) - (s[2] - s[3]);                      // :199
     const double dz = q.kz * T1;                                              // :186-187
     const double rdz = fast_rcp(dz), rT1 = fast_rcp(T1);
@@ -1236,7 +1267,7 @@ __device__ __forceinline__ void update_and_prep(const UpdateArgs& u, const PrepA
     if (i < L) {
         T1 = lv.T[i];
         const LevelPre q = pre ? *pre : level_pre(u, b, i, lv.P);
-        dT = delta_T_level(u, q, i, sums_b + i * 4, lv.T);
+        dT = delta_T_level(u, q, i, sums_b + i * 4, T1, (i == L - 1) ? T1 : lv.T[i + 1]);
     }
     if (threadIdx.x == 0) { STAMP_MAX(23); }                         // probe: dT of level 0 computed (thread 0: inactive level for emit)
     if (threadIdx.x == 1) { STAMP_MAX(25); }                         // probe: dT of level 1 computed
@@ -1319,6 +1350,8 @@ struct PostArgs {
     int do_update, do_prep;
     int axes_smem;                       // the axes of K0 are searched in shared memory
     int stage_levels;                    // T, P, mmr (and the row offsets) of the atmosphere are staged in shared memory
+    double* T_next;                      // post_level_kernel: [B][L] new temperatures of this launch
+    unsigned int* conv_count;            // post_level_kernel: [B] levels that met the convergence rule
 };
 
 // Sum `count` rows of n doubles (row stride n) element-wise with all threads of the CTA:
@@ -1473,6 +1506,193 @@ __global__ void __launch_bounds__(1024) post_kernel(PostArgs q, UpdateArgs u, Pr
                     q.stage_levels ? sm_T : nullptr, have_pre ? &pre : nullptr, q.do_prep ? sm_hasT : nullptr);
     __syncthreads();
     if (threadIdx.x == 0) { STAMP_MAX(13); }                         // records written
+}
+
+// ---------------------------------------------------------------------------
+// one CTA per level: reduction, temperature update and re-bracketing without a serial tail
+// ---------------------------------------------------------------------------
+// grid (L, B).  Everything the sweep leaves for a level — the four wavelength integrals of its
+// partial rows, the temperature step (needs only T of the level and of the level above), the new
+// brackets and weights of that level — is independent of the other levels, so each level gets a CTA:
+// no second reduction stage, no ticket between stages, and the chain "sums -> dT -> brackets ->
+// records" runs once per level in parallel instead of for all levels in one CTA (time stamps of the
+// round-1 structure, DESIGN.md 3.2: 18 us from the end of the sweep to the records; here the same
+// chain is one pass).  The partial rows of a level are contiguous (POST_PER_LEVEL layout), read with
+// 32-byte loads and summed in a fixed order: thread-strided over the rows, the warp butterfly of
+// warp_reduce4, then the warps in order — bitwise deterministic.  The new T of a level goes to
+// T_next: other CTAs still read the old T (as "the level above"); the CTA that takes the last ticket
+// of the atmosphere copies T_next to T and closes the convergence tracker.  The same-rows flag of a
+// record needs the neighbour's new bracket and is made by the sweep from the staged records.
+__global__ void __launch_bounds__(1024) post_level_kernel(PostArgs q, UpdateArgs u, PrepArgs pa) {
+    extern __shared__ double sm_pl[];            // [warps][4] | axes of K0
+    __shared__ double sm_bc[8];                  // [0..3] sums of the level, [4] new T
+    __shared__ int32_t sm_hasT[kMaxS];
+    __shared__ int is_last;
+    const int i = blockIdx.x, b = blockIdx.y, L = u.L, S = pa.S;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const int64_t li = (int64_t)b * L + i;
+    double* sm_red = sm_pl;
+    double* sm_axes = sm_pl + nw * 4;
+    // ---- before the sweep is waited for: inputs that it does not write
+    if (q.do_prep) {
+        if (q.axes_smem) stage_axes(pa.axis_P, pa.axis_T, S, pa.N_P, pa.N_T, sm_axes);
+        if (tid < S) sm_hasT[tid] = pa.has_T[tid];
+    }
+    LevelPre pre;
+    double T1 = 0.0, T2 = 0.0, Pi = 0.0, mmr_s = 0.0;
+    double trk_T = 0.0;
+    int trk_sgn = 2, trk_flips = 0, trk_ncol = 0;
+    if (q.do_update && tid == 0) {
+        pre = level_pre(u, b, i, u.P + (int64_t)b * L);
+        T1 = u.T[li];
+        T2 = (i == L - 1) ? T1 : u.T[li + 1];                            // :358-363
+        if (u.trk_T) {
+            trk_ncol = u.trk_ncol[b];
+            trk_T = u.trk_T[li];
+            trk_sgn = u.trk_state[li * 2]; trk_flips = u.trk_state[li * 2 + 1];
+        }
+    }
+    if (q.do_prep && tid < S) { Pi = pa.P[li]; mmr_s = pa.mmr[li * S + tid]; }
+    const int rows = __ldcg(q.plan_hdr);
+    if (tid == 0) { STAMP_MIN(0); STAMP_MAX(1); }
+    pdl_wait();                                  // partials come from the sweep before
+    if (tid == 0) { STAMP_MIN(2); STAMP_MAX(3); }
+    pdl_launch_dependents();                     // the next sweep's CTAs may line up behind this kernel
+    if (q.active && !q.active[b]) return;        // converged atmosphere of a batch
+    // ---- the four integrals of this level: rows x 4 contiguous doubles
+    const double2* p = reinterpret_cast<const double2*>(q.partials + li * (int64_t)rows * 4);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    constexpr int kB = 4;                        // rows per thread in flight
+    int r = tid;
+    for (; r + (kB - 1) * (int)blockDim.x < rows; r += kB * blockDim.x) {
+        double2 x[kB], y[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) { x[k] = __ldcg(p + 2 * (int64_t)(r + k * blockDim.x)); y[k] = __ldcg(p + 2 * (int64_t)(r + k * blockDim.x) + 1); }
+#pragma unroll
+        for (int k = 0; k < kB; ++k) { a0 += x[k].x; a1 += x[k].y; a2 += y[k].x; a3 += y[k].y; }
+    }
+    {
+        double2 x[kB], y[kB];
+#pragma unroll
+        for (int k = 0; k < kB; ++k) {
+            const bool in = r + k * (int)blockDim.x < rows;
+            x[k] = in ? __ldcg(p + 2 * (int64_t)(r + k * blockDim.x)) : make_double2(0.0, 0.0);
+            y[k] = in ? __ldcg(p + 2 * (int64_t)(r + k * blockDim.x) + 1) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int k = 0; k < kB; ++k)
+            if (r + k * (int)blockDim.x < rows) { a0 += x[k].x; a1 += x[k].y; a2 += y[k].x; a3 += y[k].y; }
+    }
+    const double r4 = warp_reduce4(a0, a1, a2, a3, lane);
+    if ((lane & 7) == 0) sm_red[warp * 4 + (lane >> 3)] = r4;
+    __syncthreads();
+    double s4 = 0.0;
+    if (tid < 4) {
+        for (int w = 0; w < nw; ++w) s4 += sm_red[w * 4 + tid];          // warps in order
+        if (q.peer_bufs) {
+            // fused one-shot all-reduce over the wavelength shards (flag-in-data words, see post_kernel):
+            // this CTA exchanges the four integrals of its own level
+            const int n = L * 4, e = i * 4 + tid;
+            const int par = (int)(q.epoch & 1ull);
+            const unsigned long long fl = (q.epoch & 0xffffffffull) << 32;
+            const unsigned long long bits = (unsigned long long)__double_as_longlong(s4);
+            const unsigned long long w0 = (bits & 0xffffffffull) | fl, w1 = (bits >> 32) | fl;
+            const int64_t slot = ((((int64_t)par * q.world + q.rank) * q.B + b) * n + e) * 2;
+            for (int rk = 0; rk < q.world; ++rk) {
+                const int dst = (q.rank + rk) % q.world;
+                asm volatile("st.relaxed.sys.global.v2.u64 [%0], {%1, %2};"
+                             ::"l"(q.peer_bufs[dst] + slot), "l"(w0), "l"(w1) : "memory");
+            }
+            double tot = 0.0;
+            bool timed_out = false;
+            for (int rk = 0; rk < q.world; ++rk) {
+                const unsigned long long* src =
+                    q.peer_bufs[q.rank] + ((((int64_t)par * q.world + rk) * q.B + b) * n + e) * 2;
+                unsigned long long x0 = 0, x1 = 0;
+                for (long long spins = 0;; ++spins) {
+                    asm volatile("ld.relaxed.sys.global.v2.u64 {%0, %1}, [%2];"
+                                 : "=l"(x0), "=l"(x1) : "l"(src) : "memory");
+                    if ((x0 & 0xffffffff00000000ull) == fl && (x1 & 0xffffffff00000000ull) == fl) break;
+                    if (spins > (1ll << 27)) { timed_out = true; break; }
+                }
+                tot += __longlong_as_double((long long)((x0 & 0xffffffffull) | (x1 << 32)));
+            }
+            if (timed_out && q.p2p_error) *q.p2p_error = 1;
+            s4 = tot;
+        }
+        q.sums[li * 4 + tid] = s4;
+        sm_bc[tid] = s4;
+    }
+    if (tid == 0) { STAMP_MIN(4); STAMP_MAX(5); }
+    if (!q.do_update) return;                    // reduction only (NCCL path)
+    __syncthreads();
+    // ---- temperature step of this level (thread 0)
+    int conv = 1;
+    if (tid == 0) {
+        const double dT = delta_T_level(u, pre, i, sm_bc, T1, T2);
+        const double Tn = T1 - dT;                                       // :407, :536
+        u.dT[li] = dT;
+        q.T_next[li] = Tn;
+        if (u.T_hist) u.T_hist[li] = Tn;
+        sm_bc[4] = Tn;
+        if (u.trk_T) {                                                    // per-level convergence, core.py:306-311
+            int sgn_prev = trk_sgn, flips = trk_flips;
+            if (trk_ncol > 0) {
+                const double d = Tn - trk_T;
+                const int sgn = (d != d) ? 3 : (d > 0.0) - (d < 0.0);
+                if (sgn_prev != 2 && (sgn != sgn_prev || sgn == 3)) ++flips;
+                sgn_prev = sgn;
+            }
+            u.trk_T[li] = Tn;
+            u.trk_state[li * 2] = sgn_prev;
+            u.trk_state[li * 2 + 1] = flips;
+            conv = (flips > u.n_zero_crossings) || (fabs(dT) < u.convergence_dT);
+        }
+        STAMP_MAX(11);
+    }
+    __syncthreads();
+    // ---- K0 of this level for the next sweep
+    if (q.do_prep) {
+        const double Tn = sm_bc[4];
+        const double* axP = q.axes_smem ? sm_axes : pa.axis_P;
+        const double* axT = q.axes_smem ? sm_axes + S * pa.N_P : pa.axis_T;
+        if (tid < S) (void)prep_pair(pa, b, i, tid, axP, axT, sm_hasT, Pi, Tn, mmr_s);
+        if (tid == 32) {                                                  // another warp: the two scalars of the record
+            double* rec = pa.lp.rec + li * pa.lp.rec8;
+            const double* Pb = pa.P + (int64_t)b * L;
+            const double p1 = Pb[i] * FREI_BAR;
+            const double p2 = (i == L - 1) ? p1 * (Pb[L - 2] * FREI_BAR) / (Pb[L - 3] * FREI_BAR) : Pb[i + 1] * FREI_BAR;
+            rec[0] = (p1 - p2) / pa.g[b];                                 // twostream.py:231 (identical every sweep)
+            rec[1] = (Tn > 1e-3 && Tn < 1e9) ? fast_rcp(Tn) : 1.0 / Tn;
+            reinterpret_cast<int64_t*>(rec)[2 + 5 * S] = 0;               // same-rows flag: made by the sweep
+        }
+    }
+    if (tid == 0) { STAMP_MAX(13); }
+    // ---- last CTA of the atmosphere: publish the new temperatures, close the tracker
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) {
+        if (u.trk_T && conv) atomicAdd(q.conv_count + b, 1u);
+        __threadfence();
+        is_last = (atomicAdd(q.counters + b, 1u) == (unsigned)(L - 1));
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    for (int e = tid; e < L; e += blockDim.x) u.T[(int64_t)b * L + e] = __ldcg(q.T_next + (int64_t)b * L + e);
+    if (tid == 0) {
+        if (u.trk_T) {
+            const int ncol = u.trk_ncol[b] + 1;
+            u.trk_ncol[b] = ncol;
+            const unsigned int nconv = __ldcg(q.conv_count + b);
+            if (u.direction == FREI_ABSORB && nconv == (unsigned)L && u.active) {   // core.py:317
+                u.active[b] = 0;
+                if (u.trk_iters) u.trk_iters[b] = ncol / 2;
+            }
+            q.conv_count[b] = 0u;
+        }
+        q.counters[b] = 0u;                      // self-cleaning for the next launch
+    }
 }
 
 // ---------------------------------------------------------------------------
@@ -1647,7 +1867,7 @@ int frei_b200_workspace_bytes(int32_t B, int32_t L, int32_t S, int64_t n_lam,
     if (layer_params) *layer_params = layer_params_bytes(B, L, S);
     if (partials)       // per-warp rows + chunk sums + per-atmosphere tickets
         *partials = ((int64_t)B * sweep_rows_max(n_lam) + (int64_t)B * kPostChunks) * L * 4 * 8 + round16((int64_t)B * 4) + 16 +
-                    round16(sweep_rows_max(n_lam) * 4);
+                    round16(sweep_rows_max(n_lam) * 4) + (int64_t)B * L * 8 + round16((int64_t)B * 4);
     if (sums) *sums = (int64_t)B * L * 4 * 8;
     if (dT) *dT = (int64_t)B * L * 8;
     return FREI_OK;
@@ -1857,6 +2077,22 @@ static int launch_post(const frei_table* tab, const frei_atmosphere* atm, const 
         if (rc) return rc;
         fill_prep(pa, tab, atm, ws);
     }
+#if POST_PER_LEVEL
+    {   // one CTA per level: threads ~ rows (a thread sums its rows 4 at a time), shared memory = warp sums + axes
+        q.T_next = ws_T_next(ws, atm->B, atm->L, n_lam);
+        q.conv_count = ws_conv_count(ws, atm->B, atm->L, n_lam);
+        int threads = (int)((rows_est + 31) / 32 * 32);
+        if (threads < 128) threads = 128;
+        if (threads > 1024) threads = 1024;
+        const size_t axes = do_prep ? prep_axes_bytes(tab->S, tab->N_P, tab->N_T) : 0;
+        q.axes_smem = axes > 0;
+        q.stage_levels = 0;
+        const size_t smem = (size_t)(threads / 32) * 4 * sizeof(double) + axes;
+        (void)n;
+        CUDA_TRY(launch_pdl(post_level_kernel, dim3(atm->L, atm->B), dim3(threads), smem, st, q, u, pa));
+        return FREI_OK;
+    }
+#endif
     // threads = G row groups x n columns, at least L (update) and n = 4 L (columns)
     int G = 1024 / (int)n;
     if (G < 1) return set_err(FREI_E_UNSUPPORTED, "more than 256 levels%s%s");

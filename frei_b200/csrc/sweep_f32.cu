@@ -375,7 +375,8 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
     float* sm_frec = reinterpret_cast<float*>(smem + (size_t)L * rec8) ;
     const TabT* slot = reinterpret_cast<const TabT*>(sm_frec + (PACKED ? (size_t)L * RF : 0)) + tid * V;
     const uint32_t stage = smem_u32(slot);
-    double* part = a.partials + ((int64_t)b * a.rows + blockIdx.x * kW + warp) * L * 4;
+    double* part = part_base(a.partials, b, a.rows, L, blockIdx.x * kW + warp);
+    const int64_t pstride = part_level_stride(a.rows);
     const int64_t n_lam = a.n_lam;
 
     const uint32_t bytes = (uint32_t)((size_t)L * rec8 * 8);
@@ -427,6 +428,16 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
                          : "=r"(done) : "r"(smem_u32(&bar)), "r"(0) : "memory");
         }
     }
+#if POST_PER_LEVEL
+    for (int lev = tid; lev < L; lev += THREADS) {           // same-rows flags from the staged offsets (see sweep_kernel)
+        int64_t* r1 = reinterpret_cast<int64_t*>(sm_rec + (size_t)lev * rec8);
+        int64_t same = lev > 0;
+        if (lev > 0)
+            for (int s = 0; s < S; ++s) if (r1[2 + 4 * S + s] != (r1 - rec8)[2 + 4 * S + s]) same = 0;
+        r1[2 + 5 * S] = same;
+    }
+    __syncthreads();
+#endif
     if (PACKED) {                                // the records once more, in fp32
         const int per = 4 * S + 2;
         for (int e = tid; e < L * per; e += THREADS) {
@@ -462,7 +473,7 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
     double red[4];
     auto publish = [&](int i) {
         const double r4 = reduce4(red[0], red[1], red[2], red[3], lane);
-        if ((lane & 7) == 0) part[i * 4 + (lane >> 3)] = r4;
+        if ((lane & 7) == 0) part[i * pstride + (lane >> 3)] = r4;
     };
     if (DIR == FREI_EMIT) {
         const double* rec = sm_rec + rec8;
@@ -544,7 +555,7 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
             }
         }
     }
-    if (lane < 4) part[((DIR == FREI_EMIT) ? 0 : (L - 1)) * 4 + lane] = 0.0;     // the level the sweep does not visit
+    if (lane < 4) part[((DIR == FREI_EMIT) ? 0 : (L - 1)) * pstride + lane] = 0.0;     // the level the sweep does not visit
     // The reduction kernel may become resident now.  (Not earlier: this kernel leaves room on every SM,
     // so CTAs of 1024 threads parked in griddepcontrol.wait from the start displace sweep CTAs into a
     // second wave — measured: +9 us per sweep.)
