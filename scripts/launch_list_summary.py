@@ -5,7 +5,7 @@ import csv
 import json
 import sys
 
-OURS = ('sweep_kernel', 'sweep_f32_kernel', 'post_kernel', 'prep_kernel', 'spectral_kernel',
+OURS = ('sweep_kernel', 'sweep_f32_kernel', 'post_kernel', 'post_level_kernel', 'prep_kernel', 'spectral_kernel',
         'update_prep_kernel', 'kappa_kernel', 'propagate_kernel', 'diag_kernel', 'diag_finish_kernel',
         'bin_trapz', 'regrid_kernel')   # dfma_peak_kernel is the roofline's own measurement, not the path
 rows = [r for r in csv.reader(l for l in open(sys.argv[1]) if l.startswith('"'))]
