@@ -86,7 +86,7 @@ struct SweepArgs {
     int64_t n_lam;
     int rows;                   // partial rows of the sweep = warp-chunks (set by the launcher from its plan)
     int n2;                     // fp64 kernel: chunks [0, n2) are 64 wavelengths wide, [n2, rows) 32 wide
-    int32_t* plan_hdr;          // workspace header: [0] = rows, written by the sweep, read by post_kernel
+    int32_t* plan_hdr;          // workspace header: [0] = rows, written by the sweep, read by the post kernel
     int B, L, S, N_T;
     // relay plan (fp64 kernel, single atmosphere, more chunks than resident warps): the (chunk, layer-step)
     // pairs are dealt out in equal runs of relay_quota steps per resident warp, 0 = every warp keeps

@@ -42,10 +42,9 @@ int frei_set_err(int code, const char* msg) { return set_err(code, "%s%s", msg);
     } while (0)
 
 // ---- programmatic dependent launch (PDL) ----------------------------------------------------------
-// sweep_kernel and post_kernel alternate on one stream, each consuming what the other wrote.  Both
-// are launched with programmatic stream serialisation: the next kernel's CTAs may become resident
-// while the previous kernel drains (post_kernel: while its last CTA runs the serial temperature
-// update) and block in griddepcontrol.wait — which returns when the previous grid has completed and
+// sweep_kernel and the post kernel (post_level_kernel) alternate on one stream, each consuming what
+// the other wrote.  Both are launched with programmatic stream serialisation: the next kernel's CTAs
+// may become resident while the previous kernel drains and block in griddepcontrol.wait — which returns when the previous grid has completed and
 // its writes are visible — before they touch any global data.  This hides the launch gap between
 // the four kernels of an RE iteration.  -DFREI_PDL=0 restores plain stream order.
 #ifndef FREI_PDL
@@ -219,7 +218,7 @@ __device__ __forceinline__ int64_t prep_pair(const PrepArgs& a, int b, int i, in
     return off;
 }
 
-// `has_T` = a.has_T or a copy of it in shared memory, `g` = a.g[b] (post_kernel loads both before it
+// `has_T` = a.has_T or a copy of it in shared memory, `g` = a.g[b] (the post kernel loads both before it
 // waits for the sweep: a load from global memory here is a full L2 round trip on the critical path).
 // `dpg_mine` (nullable): (p1 - p2)/g of level threadIdx.x, computed ahead of time by the caller.
 __device__ __forceinline__ void prep_block(const PrepArgs& a, int b, const double* sm_axes, const LevelView& lv,
@@ -998,10 +997,10 @@ sweep_kernel(SweepArgs a) {
     if (tid == 0) { STAMP_MIN(14 + SB); }                            // sweep CTA resident (before the wait)
     pdl_wait();                                  // records, T, active flags come from the previous kernel
     if (tid == 0) { STAMP_MIN(16 + SB); STAMP_MAX(17 + SB); }        // sweep released
-    // the row count for post_kernel, which reads it BEFORE its griddepcontrol.wait: written and fenced
+    // the row count for the post kernel, which reads it BEFORE its griddepcontrol.wait: written and fenced
     // before this CTA lets the dependent kernel be scheduled (it starts when every CTA has done so)
     if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) { a.plan_hdr[0] = a.rows; __threadfence(); }
-    if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: post_kernel may queue up behind it
+    if (gridDim.y == 1) pdl_launch_dependents(); // one resident wave: the post kernel may queue up behind it
     // converged atmosphere of a batch: nothing to do.  A single tracked atmosphere (Grid.emission_spectrum)
     // consumes the flag only after the records have arrived, so that its load overlaps theirs
     const unsigned act = a.active ? a.active[b] : 1u;
@@ -1112,7 +1111,7 @@ struct UpdateArgs {
 
 // dT of level i of atmosphere b from its four wavelength integrals s[0..3]
 // (div_bol_net_flux, convective_flux, delta_t_i, delta_temperature; twostream.py:23-43, 190-287)
-// Pressure-only part of delta_T_level: the same in every sweep of a solve.  post_kernel computes it
+// Pressure-only part of delta_T_level: the same in every sweep of a solve.  The post kernel computes it
 // before it waits for the sweep (thread i = level i), so that the loads of g, m_bar and alpha, one of
 // the two logarithms and half of the divisions are off the critical path between two sweeps.
 struct LevelPre {
@@ -1331,7 +1330,8 @@ __global__ void update_prep_kernel(UpdateArgs u, PrepArgs pa, int do_prep, const
 }
 
 // ---------------------------------------------------------------------------
-// fixed-order reduction of the per-warp partials (+ optional fused T update and re-bracketing)
+// fixed-order reduction of the per-warp partials (+ optional fused T update and re-bracketing):
+// the two-stage kernel of round 1, built with -DPOST_PER_LEVEL=0 (default: post_level_kernel below)
 // ---------------------------------------------------------------------------
 // grid (nchunks, B).  Stage 1: every CTA sums its chunk of partial rows.  The CTA that finishes
 // last for an atmosphere (atomic ticket) sums the chunk results in fixed chunk order — the

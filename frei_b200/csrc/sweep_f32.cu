@@ -367,7 +367,7 @@ __global__ void __launch_bounds__(THREADS) sweep_f32_kernel(SweepArgs a) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int b = blockIdx.y;
     asm volatile("griddepcontrol.wait;" ::: "memory");                  // records, T, flags: previous kernel
-    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by post_kernel
+    if (a.plan_hdr && blockIdx.x == 0 && b == 0 && tid == 0) a.plan_hdr[0] = a.rows;   // read by the post kernel
     if (a.active && !a.active[b]) return;
     const int L = a.L, S = a.S, rec8 = a.lp.rec8;
     double* sm_rec = smem;
