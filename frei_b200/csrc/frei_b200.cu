@@ -1538,12 +1538,12 @@ __global__ void __launch_bounds__(1024) post_level_kernel(PostArgs q, UpdateArgs
         if (q.axes_smem) stage_axes(pa.axis_P, pa.axis_T, S, pa.N_P, pa.N_T, sm_axes);
         if (tid < S) sm_hasT[tid] = pa.has_T[tid];
     }
-    LevelPre pre;
+    __shared__ LevelPre sm_pre;                  // thread 0's pressure-only terms (kept out of its registers)
     double T1 = 0.0, T2 = 0.0, Pi = 0.0, mmr_s = 0.0;
     double trk_T = 0.0;
     int trk_sgn = 2, trk_flips = 0, trk_ncol = 0;
     if (q.do_update && tid == 0) {
-        pre = level_pre(u, b, i, u.P + (int64_t)b * L);
+        sm_pre = level_pre(u, b, i, u.P + (int64_t)b * L);
         T1 = u.T[li];
         T2 = (i == L - 1) ? T1 : u.T[li + 1];                            // :358-363
         if (u.trk_T) {
@@ -1563,25 +1563,20 @@ __global__ void __launch_bounds__(1024) post_level_kernel(PostArgs q, UpdateArgs
     const double2* p = reinterpret_cast<const double2*>(q.partials + li * (int64_t)rows * 4);
     double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
     constexpr int kB = 4;                        // rows per thread in flight
-    int r = tid;
-    for (; r + (kB - 1) * (int)blockDim.x < rows; r += kB * blockDim.x) {
-        double2 x[kB], y[kB];
-#pragma unroll
-        for (int k = 0; k < kB; ++k) { x[k] = __ldcg(p + 2 * (int64_t)(r + k * blockDim.x)); y[k] = __ldcg(p + 2 * (int64_t)(r + k * blockDim.x) + 1); }
-#pragma unroll
-        for (int k = 0; k < kB; ++k) { a0 += x[k].x; a1 += x[k].y; a2 += y[k].x; a3 += y[k].y; }
-    }
-    {
+    // the same number of load batches for every thread of the CTA (C2: 3125 rows = one batch of up to
+    // four rows per thread); a thread adds its rows in ascending order
+    for (int base = tid; base < rows + tid; base += kB * (int)blockDim.x) {
         double2 x[kB], y[kB];
 #pragma unroll
         for (int k = 0; k < kB; ++k) {
-            const bool in = r + k * (int)blockDim.x < rows;
-            x[k] = in ? __ldcg(p + 2 * (int64_t)(r + k * blockDim.x)) : make_double2(0.0, 0.0);
-            y[k] = in ? __ldcg(p + 2 * (int64_t)(r + k * blockDim.x) + 1) : make_double2(0.0, 0.0);
+            const int rr = base + k * (int)blockDim.x;
+            const bool in = rr < rows;
+            x[k] = in ? __ldcg(p + 2 * (int64_t)rr) : make_double2(0.0, 0.0);
+            y[k] = in ? __ldcg(p + 2 * (int64_t)rr + 1) : make_double2(0.0, 0.0);
         }
 #pragma unroll
         for (int k = 0; k < kB; ++k)
-            if (r + k * (int)blockDim.x < rows) { a0 += x[k].x; a1 += x[k].y; a2 += y[k].x; a3 += y[k].y; }
+            if (base + k * (int)blockDim.x < rows) { a0 += x[k].x; a1 += x[k].y; a2 += y[k].x; a3 += y[k].y; }
     }
     const double r4 = warp_reduce4(a0, a1, a2, a3, lane);
     if ((lane & 7) == 0) sm_red[warp * 4 + (lane >> 3)] = r4;
@@ -1629,7 +1624,7 @@ __global__ void __launch_bounds__(1024) post_level_kernel(PostArgs q, UpdateArgs
     // ---- temperature step of this level (thread 0)
     int conv = 1;
     if (tid == 0) {
-        const double dT = delta_T_level(u, pre, i, sm_bc, T1, T2);
+        const double dT = delta_T_level(u, sm_pre, i, sm_bc, T1, T2);
         const double Tn = T1 - dT;                                       // :407, :536
         u.dT[li] = dT;
         q.T_next[li] = Tn;
